@@ -1,0 +1,218 @@
+/*
+ * mops_b200.h -- C ABI of the B200-native particle-advection / remap engine.
+ *
+ * This is the drop-in boundary for the hot path of YosefQiu/MOPS (reference paths below
+ * are relative to the reference root).  The innermost stable seam of the reference is
+ *
+ *   MOPS::Factory::StreamLine / PathLine / VisualizeFixedDepth     src/Common/MOPSFactory.h:9-40
+ *   MOPS::Factory::CalcCellVertexZtop / ...Velocity / ...ToVertex  src/Common/MOPSFactory.h:42-106
+ *   MPASOField::calcInWhichCells / MPASOGrid::searchKDT            src/Core/MPASOField.cpp:23-34
+ *
+ * reached from MOPSApp::runStreamLine / runPathLine / runRemapping / addSol
+ * (src/Core/MOPSApp.cpp:77-137, 171-196, 231-290).  Every entry point here replaces one of
+ * those calls; INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ * The C++ drop-in of include/api/MOPS.h that ships in this repo (include/api/MOPS.h) is a
+ * thin host layer over exactly these functions.
+ *
+ * Conventions
+ *  - plain pointers and sizes, no C++ / torch types; every function returns 0 on success
+ *    or a negative MOPS_E_* code, and mops_last_error(ctx) gives the message.  Nothing
+ *    throws across the boundary.  There is NO CPU fallback: without a CUDA device (or if
+ *    the sm_100a kernels cannot be loaded) mops_create fails.
+ *  - one context = one GPU = one caller thread at a time (the reference API is not
+ *    re-entrant either).  Multi-GPU = one context per process/GPU with the
+ *    mesh replicated and particles sharded by the caller (bench.py, torch.distributed).
+ *  - connectivity is passed exactly as MPAS files / MPASOGrid hold it: int32, 1-based,
+ *    0-padded rows of width maxEdges (src/IO/MPASOReader.cpp:147-153).  Cell ids that
+ *    cross this boundary in either direction are 0-based indices into the caller's cell
+ *    arrays (what searchKDT returns); the engine's internal renumbering is invisible.
+ *  - vec3 arrays are [n][3] doubles (the 24-byte layout of the reference's vec3).
+ *  - `mem` selects whether particle / image buffers are HOST or DEVICE pointers.  Mesh and
+ *    snapshot inputs are always host pointers (pinned memory makes their upload async).
+ */
+#ifndef MOPS_B200_H
+#define MOPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOPS_B200_ABI_VERSION 1
+
+typedef struct mops_ctx mops_ctx;
+
+enum {
+    MOPS_OK = 0,
+    MOPS_E_INVALID = -1,  /* bad argument / call order (reference: Error(...) + empty result) */
+    MOPS_E_CUDA = -2,     /* CUDA runtime error; message in mops_last_error                   */
+    MOPS_E_NODEVICE = -3, /* no usable sm_100-class device: there is no CPU fallback          */
+    MOPS_E_NOMEM = -4,
+    MOPS_E_STATE = -5     /* mesh / snapshot not set                                          */
+};
+
+enum { MOPS_MEM_HOST = 0, MOPS_MEM_DEVICE = 1 };
+
+/* CalcMethodType / CalcDirection of the reference, src/Core/MPASOVisualizer.h:16-17 */
+enum { MOPS_METHOD_RK4 = 0, MOPS_METHOD_EULER = 1 };
+enum { MOPS_DIR_FORWARD = 0, MOPS_DIR_BACKWARD = 1 };
+
+/* why a particle stopped (the reference's kernels just `return`) */
+enum {
+    MOPS_ST_ALIVE = 0,
+    MOPS_ST_BAD_CELL = 1,      /* start cell out of range            VK:895,903        */
+    MOPS_ST_NOT_IN_CELL = 2,   /* IsInMesh false at an RK stage      VK:753-756        */
+    MOPS_ST_BAD_COLUMN = 3,    /* |z_up - z_dn| < 1e-12 ...          VK:833            */
+    MOPS_ST_ZERO_VELOCITY = 4, /* |v| < 1e-12 (streamline only)      VK:845-852        */
+    MOPS_ST_ABOVE_SURFACE = 5, /* pathline above-surface branch (reads ztop[-1] in the reference; not replicated) */
+    MOPS_ST_BAD_SETUP = 6
+};
+
+#define MOPS_MAX_SNAPSHOT_SLOTS 4
+#define MOPS_MAX_ATTRS 2 /* the reference's kernels use the first two scalar attributes (R11) */
+
+/* ---- lifetime --------------------------------------------------------------------- */
+/* replaces MOPS_Init("gpu") device selection, src/Core/MOPSApp.cpp:34-63 */
+int mops_create(mops_ctx** out, int device_ordinal);
+void mops_destroy(mops_ctx* ctx);
+const char* mops_last_error(const mops_ctx* ctx);
+int mops_abi_version(void);
+/* pinned host staging for snapshot double-buffering (cudaHostAlloc / cudaFreeHost) */
+int mops_host_alloc(void** out, size_t bytes);
+int mops_host_free(void* p);
+int mops_synchronize(mops_ctx* ctx);
+
+/* ---- mesh: replaces MOPSApp::addGrid + the per-call mesh H2D of the reference's CUDA
+ *      wrappers (src/Core/MOPSApp.cpp:65-75; src/GPU/CUDA/Kernel/MPASOVisualizerKernels.cu:1369-1383).
+ *      Uploaded once, renumbered along a Morton curve and kept resident in HBM. ------- */
+int mops_set_mesh(mops_ctx* ctx, int32_t n_cells, int32_t n_vertices, int32_t max_edges,
+                  const double* cell_xyz,            /* [n_cells][3]                          */
+                  const double* vertex_xyz,          /* [n_vertices][3]                       */
+                  const int32_t* vertices_on_cell,   /* [n_cells][max_edges] 1-based, 0 pad   */
+                  const int32_t* cells_on_cell,      /* [n_cells][max_edges] 1-based, 0 pad   */
+                  const int32_t* cells_on_vertex,    /* [n_vertices][3] 1-based               */
+                  const int32_t* n_edges_on_cell);   /* [n_cells]                             */
+
+/* ---- snapshot: replaces MOPSApp::addSol's preprocessing chain (calcCellCenterZtop,
+ *      calcCellVertexZtop, calcCellCenterVelocityByZM, calcCellVertexVelocity,
+ *      calcCellVertexVertVelocity, calcCellCenterToVertex; src/Core/MOPSApp.cpp:100-130),
+ *      run on the device.  Inputs are cell-major [n_cells][n_levels] host arrays as
+ *      MPASOSolution holds them; vert_vel_top is [n_cells][n_levels+1] or NULL (zeros).
+ *      attrs: n_attr cell-major scalar fields in the reference's std::map (alphabetical)
+ *      order; n_attr_total is mDoubleAttributes.size() (gates the attribute image /
+ *      pathline attributes exactly as `size() > 1` does, VK:259-267, 1093-1104).
+ *      The async form enqueues upload + preprocessing on the context's side stream and
+ *      returns; the next call that uses `slot` waits on it (double-buffered pathlines). */
+int mops_set_snapshot(mops_ctx* ctx, int32_t slot, int32_t n_levels,
+                      const double* zonal, const double* meridional, const double* layer_thickness,
+                      const double* bottom_depth, const double* vert_vel_top,
+                      int32_t n_attr, const double* const* attrs, int32_t n_attr_total);
+int mops_set_snapshot_async(mops_ctx* ctx, int32_t slot, int32_t n_levels,
+                            const double* zonal, const double* meridional, const double* layer_thickness,
+                            const double* bottom_depth, const double* vert_vel_top,
+                            int32_t n_attr, const double* const* attrs, int32_t n_attr_total);
+int mops_snapshot_wait(mops_ctx* ctx, int32_t slot);
+/* copy the prepared vertex-major arrays back in the caller's vertex order (parity tests):
+ * ztop [nV][L], vel [nV][L][3], vertvel [nV][L+1] (level L is not kept by the engine and
+ * reads back as 0 -- no kernel of the path uses it), attr [nV][L].  Any may be NULL.     */
+int mops_get_prepared(mops_ctx* ctx, int32_t slot, double* ztop_vertex, double* vel_vertex,
+                      double* vertvel_vertex, double* attr0_vertex, double* attr1_vertex);
+
+/* ---- point location: replaces MPASOField::calcInWhichCells (host, serial nanoflann 1-NN;
+ *      src/Core/MPASOField.cpp:23-34, src/Core/MPASOGrid.cpp:287-313).  Exact nearest cell
+ *      centre by a cooperative cellsOnCell walk started from a lat/lon bucket table.      */
+int mops_locate(mops_ctx* ctx, int32_t mem, int64_t n, const double* xyz, int32_t* cell_out);
+
+/* ---- trajectories ----------------------------------------------------------------- */
+typedef struct mops_traj_cfg {
+    int32_t method;         /* MOPS_METHOD_*   (TrajectorySettings::methodType)              */
+    int32_t direction;      /* MOPS_DIR_*      (TrajectorySettings::directionType)           */
+    int64_t delta_t;        /* seconds         (TrajectorySettings::deltaT)                  */
+    int64_t duration;       /* seconds         (TrajectorySettings::simulationDuration)      */
+    int64_t record_t;       /* seconds         (TrajectorySettings::recordT)                 */
+    int32_t mem;            /* MOPS_MEM_*: space of all particle / output pointers           */
+    int32_t sort_particles; /* 1: process particles in Morton-cell order (results unchanged) */
+    int32_t reserved[4];
+} mops_traj_cfg;
+
+typedef struct mops_traj_io {
+    int64_t n;              /* particles                                                      */
+    double* xyz;            /* [n][3]  in: seeds, out: end points (stable_points)             */
+    float* depth;           /* [n]     in/out per-particle depth, float as in the reference (R3) */
+    const int32_t* cell0;   /* [n] start cells or NULL (then located on the device)           */
+    double* out_pos;        /* [n][each][3] recorded positions, each = duration / record_t    */
+    double* out_vel;        /* [n][each][3] recorded velocities                               */
+    double* out_attr;       /* [n][each][3] pathline attributes (x,y used) or NULL            */
+    int32_t* out_cell_log;  /* [n][steps] cell of every step (-1 = not executed) or NULL      */
+    int32_t* out_status;    /* [n] MOPS_ST_* or NULL                                          */
+    int32_t* out_steps;     /* [n] steps started (alive at step start) or NULL                */
+    int32_t* out_cell;      /* [n] last cell or NULL                                          */
+} mops_traj_io;
+
+typedef struct mops_traj_stats {
+    int64_t particle_steps; /* sum of steps started over all particles                        */
+    int64_t alive_at_end;
+    double kernel_ms;       /* CUDA-event time of the advection kernel(s)                     */
+    double locate_ms;
+    double total_ms;        /* whole call on the stream (copies included)                     */
+    int32_t launches;       /* kernels of this library launched by the call                   */
+    int32_t reserved;
+} mops_traj_stats;
+
+/* replaces MOPS::Factory::StreamLine (src/Common/MOPSFactory.h:28-33 -> VK:653-1015) */
+int mops_streamline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io,
+                    mops_traj_stats* stats);
+/* replaces MOPS::Factory::PathLine (src/Common/MOPSFactory.h:35-40 -> VK:1017-1496) */
+int mops_pathline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot,
+                  const mops_traj_io* io, mops_traj_stats* stats);
+
+/* host-side line assembly + NaN trimming (src/Common/TrajectoryCommon.h:43-190; R7, R8):
+ * raw [n][each][3] -> points / velocity [n][each+1][3], temperature / salinity [n][each+1]
+ * (may be NULL), last [n][3].  pathline_mode fills temperature/salinity as the reference
+ * does (from velocity.x / velocity.y).  Pure host function. */
+int mops_finalize_lines(int64_t n, int32_t each, const double* seeds, const double* raw_pos, const double* raw_vel,
+                        int32_t pathline_mode, double* points, double* velocity, double* temperature,
+                        double* salinity, double* last);
+
+/* ---- remap ---------------------------------------------------------------------------- */
+typedef struct mops_remap_cfg {
+    int32_t width, height;      /* VisualizationSettings::imageSize (x = width, y = height)   */
+    double lat_min, lat_max;    /* LatRange */
+    double lon_min, lon_max;    /* LonRange */
+    double fixed_depth;         /* FixedDepth (positive down)                                 */
+    int32_t mem;                /* MOPS_MEM_* for img0 / img1 / pixel_cell                    */
+    int32_t reserved[3];
+} mops_remap_cfg;
+
+typedef struct mops_remap_stats {
+    double kernel_ms;           /* locate + interpolate kernel                                */
+    double total_ms;
+    int64_t nan_pixels;
+    int32_t launches;
+    int32_t n_images;           /* 1, or 2 when the attribute image is produced               */
+} mops_remap_stats;
+
+/* replaces MOPS::Factory::VisualizeFixedDepth incl. its host KD-tree loop
+ * (src/Common/MOPSFactory.h:15-19 -> VK:238-471, TBBKernel::SearchKDTree).
+ * img0/img1: [height][width][4] doubles; img1 / pixel_cell may be NULL. */
+int mops_remap_fixed_depth(mops_ctx* ctx, const mops_remap_cfg* cfg, int32_t slot,
+                           double* img0, double* img1, int32_t* pixel_cell, mops_remap_stats* stats);
+
+/* ---- introspection ---------------------------------------------------------------- */
+typedef struct mops_info {
+    int32_t device, sm_count, cc_major, cc_minor;
+    int64_t l2_bytes, hbm_bytes;
+    int64_t mesh_bytes, snapshot_bytes[MOPS_MAX_SNAPSHOT_SLOTS];
+    int32_t record_width;       /* compile-time vertex capacity of the resident cell records  */
+    int32_t n_levels;
+    int64_t total_launches;     /* kernels of this library launched since mops_create         */
+    int32_t nonmonotone_cells[MOPS_MAX_SNAPSHOT_SLOTS]; /* cells taking the full-column path  */
+} mops_info;
+int mops_get_info(mops_ctx* ctx, mops_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOPS_B200_H */

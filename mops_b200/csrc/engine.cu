@@ -1,0 +1,1011 @@
+// engine.cu -- host side of the C ABI declared in include/mops_b200.h: resident mesh and
+// snapshot management, stream / event plumbing, kernel launches.  No CPU fallback: every
+// compute entry point launches sm_100a kernels from kernels.cuh or fails.
+#include "../../include/mops_b200.h"
+#include "kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace mops;
+
+namespace {
+
+struct Snapshot {
+    bool valid = false;
+    int L = 0;
+    int n_attr = 0, n_attr_total = 0;
+    double* ztop = nullptr;
+    double4* velw = nullptr;
+    double* attr[MOPS_MAX_ATTRS] = {nullptr, nullptr};
+    unsigned char* mono = nullptr;
+    int nonmono = 0;
+    size_t bytes = 0;
+    cudaEvent_t ready = nullptr;    // recorded on the side stream after preprocessing
+    cudaEvent_t last_use = nullptr; // recorded on the main stream after the last kernel reading the slot
+    bool pending = false;
+    bool used = false;
+};
+
+struct Buf { // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct mops_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_kend = nullptr, ev_end = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // mesh
+    bool has_mesh = false;
+    int nC = 0, nV = 0, maxEdges = 0, M = 0, F = 0;
+    double radius = 0.0;
+    void* rec = nullptr;
+    double4* c4 = nullptr;
+    double4* trig = nullptr;      // caller cell order
+    VertRec* vert = nullptr;      // internal vertex order
+    int* vcell_ext = nullptr;     // [nV][3] caller cell ids of each internal vertex
+    int *c_int2ext = nullptr, *c_ext2int = nullptr, *v_int2ext = nullptr, *v_ext2int = nullptr;
+    int* cube = nullptr;
+    size_t mesh_bytes = 0;
+
+    Snapshot snap[MOPS_MAX_SNAPSHOT_SLOTS];
+    // staging for snapshot upload (caller cell order), reused by every snapshot on the side stream
+    Buf st_zonal, st_merid, st_thick, st_wtop, st_bottom, st_ztopc, st_attr, st_vmono;
+    int* d_nonmono = nullptr;
+    // particle scratch (host-memory mode) + sort scratch
+    Buf p_xyz, p_depth, p_cell0, p_cell_int, p_out_pos, p_out_vel, p_out_attr, p_log, p_status, p_steps, p_fcell;
+    Buf s_keys, s_vals, s_keys2, s_vals2, s_tmp;
+    Buf r_img0, r_img1, r_cells;
+    unsigned long long* counters = nullptr; // [4]
+};
+
+namespace {
+
+int fail(mops_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, MOPS_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+int ensure(mops_ctx* ctx, Buf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return MOPS_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(ctx, MOPS_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = bytes;
+    return MOPS_OK;
+}
+
+inline int blocks_for(long long n, int bs) { return (int)((n + bs - 1) / bs); }
+
+// 63-bit Morton key of a point in the unit cube
+inline uint64_t spread21(uint64_t x)
+{
+    x &= 0x1fffffULL;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+
+void morton_order(const double* xyz, int n, std::vector<int>& int2ext)
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], xyz[3 * (size_t)i + a]);
+            hi[a] = std::max(hi[a], xyz[3 * (size_t)i + a]);
+        }
+    double ext = 1e-300;
+    for (int a = 0; a < 3; ++a) ext = std::max(ext, hi[a] - lo[a]);
+    std::vector<uint64_t> key(n);
+    for (int i = 0; i < n; ++i) {
+        uint64_t q[3];
+        for (int a = 0; a < 3; ++a) {
+            double t = (xyz[3 * (size_t)i + a] - lo[a]) / ext;
+            t = std::min(std::max(t, 0.0), 1.0);
+            q[a] = (uint64_t)(t * 2097151.0);
+        }
+        key[i] = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+    }
+    int2ext.resize(n);
+    std::iota(int2ext.begin(), int2ext.end(), 0);
+    std::stable_sort(int2ext.begin(), int2ext.end(), [&](int a, int b) { return key[a] < key[b]; });
+}
+
+template <int M>
+int upload_records(mops_ctx* ctx, const double* vertex_xyz, const int32_t* voc, const int32_t* coc, const int32_t* nedges,
+                   const std::vector<int>& c_int2ext, const std::vector<int>& c_ext2int, const std::vector<int>& v_ext2int)
+{
+    const int nC = ctx->nC, nV = ctx->nV, E = ctx->maxEdges;
+    std::vector<CellRec<M>> h((size_t)nC);
+    for (int ci = 0; ci < nC; ++ci) {
+        const int ce = c_int2ext[ci];
+        CellRec<M>& r = h[ci];
+        std::memset(&r, 0, sizeof(r));
+        int nv = nedges[ce];
+        if (nv < 0 || nv > M || nv > E) nv = 0; // unusable cell: every evaluation in it fails (VK:748-751)
+        r.nv = nv;
+        for (int k = 0; k < M; ++k) {
+            r.vid[k] = -1;
+            r.nbr[k] = -1;
+        }
+        for (int k = 0; k < nv; ++k) {
+            const int ve = voc[(size_t)ce * E + k] - 1;
+            if (ve < 0 || ve >= nV) return fail(ctx, MOPS_E_INVALID, "verticesOnCell[%d][%d] = %d out of range", ce, k, ve + 1);
+            r.vid[k] = v_ext2int[ve];
+            r.vx[k] = vertex_xyz[3 * (size_t)ve];
+            r.vy[k] = vertex_xyz[3 * (size_t)ve + 1];
+            r.vz[k] = vertex_xyz[3 * (size_t)ve + 2];
+            const int ne = coc[(size_t)ce * E + k] - 1; // 0 pad -> -1 -> skipped, as VK:909-912
+            r.nbr[k] = (ne >= 0 && ne < nC) ? c_ext2int[ne] : -1;
+        }
+    }
+    CK(cudaMalloc(&ctx->rec, sizeof(CellRec<M>) * (size_t)nC));
+    ctx->mesh_bytes += sizeof(CellRec<M>) * (size_t)nC;
+    CK(cudaMemcpyAsync(ctx->rec, h.data(), sizeof(CellRec<M>) * (size_t)nC, cudaMemcpyHostToDevice, ctx->stream));
+    k_build_records<M><<<blocks_for(nC, 128), 128, 0, ctx->stream>>>(reinterpret_cast<CellRec<M>*>(ctx->rec), nC);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream)); // h goes out of scope
+    return MOPS_OK;
+}
+
+template <int M>
+int build_cube(mops_ctx* ctx)
+{
+    // finest resolution: about one bucket per two cells
+    int F = 1;
+    while (6LL * (2 * F) * (2 * F) <= (long long)ctx->nC / 2 && F < 2048) F *= 2;
+    size_t total = 0;
+    for (int f = 1; f <= F; f *= 2) total += 6ULL * f * f;
+    int* all = nullptr;
+    CK(cudaMalloc(&all, total * sizeof(int)));
+    ctx->mesh_bytes += total * sizeof(int);
+    int* parent = nullptr;
+    int* cur = all;
+    for (int f = 1; f <= F; f *= 2) {
+        k_cube_level<M><<<blocks_for(6LL * f * f, 128), 128, 0, ctx->stream>>>(
+            reinterpret_cast<const CellRec<M>*>(ctx->rec), ctx->c4, parent, cur, f, ctx->radius);
+        ctx->launches++;
+        parent = cur;
+        cur += 6ULL * f * f;
+    }
+    CK(cudaGetLastError());
+    ctx->cube = parent; // finest level (coarser levels stay allocated in the same block)
+    ctx->F = F;
+    return MOPS_OK;
+}
+
+void free_mesh(mops_ctx* c)
+{
+    // the cube table is one allocation whose finest level is the last slice
+    if (c->cube) {
+        size_t before = 0;
+        for (int f = 1; f < c->F; f *= 2) before += 6ULL * f * f;
+        cudaFree(c->cube - before);
+    }
+    cudaFree(c->rec); cudaFree(c->c4); cudaFree(c->trig); cudaFree(c->vert); cudaFree(c->vcell_ext);
+    cudaFree(c->c_int2ext); cudaFree(c->c_ext2int); cudaFree(c->v_int2ext); cudaFree(c->v_ext2int);
+    c->cube = nullptr; c->rec = nullptr; c->c4 = nullptr; c->trig = nullptr; c->vert = nullptr; c->vcell_ext = nullptr;
+    c->c_int2ext = c->c_ext2int = c->v_int2ext = c->v_ext2int = nullptr;
+    c->has_mesh = false;
+    c->mesh_bytes = 0;
+}
+
+void free_snapshot(Snapshot& s)
+{
+    cudaFree(s.ztop); cudaFree(s.velw); cudaFree(s.attr[0]); cudaFree(s.attr[1]); cudaFree(s.mono);
+    s.ztop = nullptr; s.velw = nullptr; s.attr[0] = s.attr[1] = nullptr; s.mono = nullptr;
+    s.valid = false; s.bytes = 0; s.L = 0;
+}
+
+SnapView view_of(const Snapshot& s)
+{
+    SnapView v;
+    v.ztop = s.ztop; v.velw = s.velw; v.attr0 = s.attr[0]; v.attr1 = s.attr[1]; v.mono = s.mono;
+    return v;
+}
+
+int wait_slot(mops_ctx* ctx, int slot)
+{
+    Snapshot& s = ctx->snap[slot];
+    if (s.pending) {
+        CK(cudaStreamWaitEvent(ctx->stream, s.ready, 0));
+        s.pending = false;
+    }
+    return MOPS_OK;
+}
+
+int mark_use(mops_ctx* ctx, int slot)
+{
+    Snapshot& s = ctx->snap[slot];
+    CK(cudaEventRecord(s.last_use, ctx->stream));
+    s.used = true;
+    return MOPS_OK;
+}
+
+template <int M>
+int launch_cell_mono(mops_ctx* ctx, Snapshot& s, int slot, cudaStream_t st)
+{
+    k_cell_mono<M><<<blocks_for(ctx->nC, 256), 256, 0, st>>>(reinterpret_cast<const CellRec<M>*>(ctx->rec),
+                                                             (const unsigned char*)ctx->st_vmono.p, s.mono, ctx->nC, ctx->d_nonmono + slot);
+    ctx->launches++;
+    return MOPS_OK;
+}
+
+int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const double* merid, const double* thick,
+                      const double* bottom, const double* wtop, int n_attr, const double* const* attrs, int n_attr_total,
+                      bool async)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "mops_set_snapshot: no mesh");
+    if (slot < 0 || slot >= MOPS_MAX_SNAPSHOT_SLOTS) return fail(ctx, MOPS_E_INVALID, "slot %d out of range", slot);
+    if (L < 2 || L > 100) return fail(ctx, MOPS_E_INVALID, "n_levels %d outside [2,100] (reference MAX_VERTICAL_LEVEL_NUM)", L);
+    if (!zonal || !merid || !thick || !bottom) return fail(ctx, MOPS_E_INVALID, "null snapshot input");
+    if (n_attr < 0 || n_attr > MOPS_MAX_ATTRS) return fail(ctx, MOPS_E_INVALID, "n_attr %d outside [0,%d]", n_attr, MOPS_MAX_ATTRS);
+    if ((long long)ctx->nV * L >= (1LL << 31)) return fail(ctx, MOPS_E_INVALID, "nVertices*nLevels exceeds 2^31");
+    CK(cudaSetDevice(ctx->device));
+    Snapshot& s = ctx->snap[slot];
+    const size_t nC = (size_t)ctx->nC, nV = (size_t)ctx->nV;
+    cudaStream_t st = ctx->side;
+
+    // the slot may still be read by kernels on the main stream
+    if (s.used) CK(cudaStreamWaitEvent(st, s.last_use, 0));
+    if (s.valid && s.L != L) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(st));
+        free_snapshot(s);
+    }
+    if (!s.ztop) {
+        CK(cudaMalloc(&s.ztop, nV * L * sizeof(double)));
+        CK(cudaMalloc(&s.velw, nV * L * sizeof(double4)));
+        CK(cudaMalloc(&s.mono, nC));
+        s.bytes = nV * L * (sizeof(double) + sizeof(double4)) + nC;
+    }
+    for (int a = 0; a < MOPS_MAX_ATTRS; ++a) {
+        if (a < n_attr && !s.attr[a]) {
+            CK(cudaMalloc(&s.attr[a], nV * L * sizeof(double)));
+            s.bytes += nV * L * sizeof(double);
+        }
+    }
+    s.L = L;
+    s.n_attr = n_attr;
+    s.n_attr_total = n_attr_total;
+
+    int rc;
+    if ((rc = ensure(ctx, ctx->st_zonal, nC * L * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->st_merid, nC * L * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->st_thick, nC * L * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->st_ztopc, nC * L * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->st_bottom, nC * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->st_vmono, nV))) return rc;
+    if (wtop && (rc = ensure(ctx, ctx->st_wtop, nC * (L + 1) * 8))) return rc;
+    if (n_attr > 0 && (rc = ensure(ctx, ctx->st_attr, nC * L * 8))) return rc;
+
+    CK(cudaMemcpyAsync(ctx->st_zonal.p, zonal, nC * L * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->st_merid.p, merid, nC * L * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->st_thick.p, thick, nC * L * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->st_bottom.p, bottom, nC * 8, cudaMemcpyHostToDevice, st));
+    if (wtop) CK(cudaMemcpyAsync(ctx->st_wtop.p, wtop, nC * (L + 1) * 8, cudaMemcpyHostToDevice, st));
+
+    k_cell_ztop<<<blocks_for(ctx->nC, 128), 128, 0, st>>>((const double*)ctx->st_thick.p, (const double*)ctx->st_bottom.p,
+                                                          (double*)ctx->st_ztopc.p, ctx->nC, L);
+    k_vertex_fields<<<blocks_for((long long)nV * L, 256), 256, 0, st>>>(
+        ctx->vert, ctx->vcell_ext, ctx->trig, (const double*)ctx->st_ztopc.p, (const double*)ctx->st_zonal.p,
+        (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L);
+    ctx->launches += 2;
+    for (int a = 0; a < n_attr; ++a) {
+        CK(cudaMemcpyAsync(ctx->st_attr.p, attrs[a], nC * L * 8, cudaMemcpyHostToDevice, st));
+        k_vertex_scalar<<<blocks_for((long long)nV * L, 256), 256, 0, st>>>(ctx->vert, ctx->vcell_ext, (const double*)ctx->st_attr.p,
+                                                                          s.attr[a], ctx->nV, L);
+        ctx->launches++;
+    }
+    CK(cudaMemsetAsync(ctx->d_nonmono + slot, 0, sizeof(int), st));
+    k_vertex_mono<<<blocks_for((long long)nV * 32, 256), 256, 0, st>>>(s.ztop, (unsigned char*)ctx->st_vmono.p, ctx->nV, L);
+    ctx->launches++;
+    switch (ctx->M) {
+    case 6: launch_cell_mono<6>(ctx, s, slot, st); break;
+    case 8: launch_cell_mono<8>(ctx, s, slot, st); break;
+    default: launch_cell_mono<20>(ctx, s, slot, st); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s.ready, st));
+    s.valid = true;
+    s.pending = true;
+    s.used = false;
+    if (!async) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(&s.nonmono, ctx->d_nonmono + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        s.pending = false;
+    } else {
+        s.nonmono = -1;
+    }
+    return MOPS_OK;
+}
+
+template <int M>
+void launch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cell_int, int* d_cell_ext)
+{
+    k_locate<M><<<blocks_for(n * 8, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const CellRec<M>*>(ctx->rec), ctx->c4, ctx->cube,
+                                                                 ctx->F, ctx->nC, n, d_xyz, d_cell_int, d_cell_ext, ctx->c_int2ext);
+    ctx->launches++;
+}
+
+void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cell_int, int* d_cell_ext)
+{
+    switch (ctx->M) {
+    case 6: launch_locate<6>(ctx, n, d_xyz, d_cell_int, d_cell_ext); break;
+    case 8: launch_locate<8>(ctx, n, d_xyz, d_cell_int, d_cell_ext); break;
+    default: launch_locate<20>(ctx, n, d_xyz, d_cell_int, d_cell_ext); break;
+    }
+}
+
+template <int M>
+void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
+{
+    const int grid = blocks_for(P.n, 128);
+    if (path) k_advect<M, true><<<grid, 128, 0, ctx->stream>>>(P);
+    else k_advect<M, false><<<grid, 128, 0, ctx->stream>>>(P);
+    ctx->launches++;
+}
+
+int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back, const mops_traj_io* io, mops_traj_stats* stats,
+                    bool path)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (!cfg || !io) return fail(ctx, MOPS_E_INVALID, "null cfg/io");
+    if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "no mesh");
+    if (front < 0 || front >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[front].valid) return fail(ctx, MOPS_E_STATE, "snapshot slot %d not set", front);
+    if (path && (back < 0 || back >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[back].valid)) return fail(ctx, MOPS_E_STATE, "snapshot slot %d not set", back);
+    // reference: Error("invalid trajectory settings") + empty result (VK:666-669, 1030-1033)
+    if (cfg->delta_t <= 0 || cfg->record_t <= 0 || cfg->duration <= 0) return fail(ctx, MOPS_E_INVALID, "invalid trajectory settings");
+    if (cfg->delta_t > 0x7fffffffLL || cfg->record_t > 0x7fffffffLL || cfg->duration > 0x7fffffffLL)
+        return fail(ctx, MOPS_E_INVALID, "trajectory settings exceed the reference's int range");
+    const long long n = io->n;
+    if (n < 0 || n > 0x7fffffffLL) return fail(ctx, MOPS_E_INVALID, "particle count out of range");
+    const int each = (int)(cfg->duration / cfg->record_t);
+    const int times = (int)(cfg->duration / cfg->delta_t);
+    if (each <= 0 || times <= 0) return fail(ctx, MOPS_E_INVALID, "invalid integration steps"); // VK:709-712
+    if (n == 0) {
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        return MOPS_OK;
+    }
+    if (!io->xyz || !io->depth || !io->out_pos || !io->out_vel) return fail(ctx, MOPS_E_INVALID, "null particle buffers");
+    Snapshot& F = ctx->snap[front];
+    Snapshot& B = ctx->snap[path ? back : front];
+    if (path && F.L != B.L) return fail(ctx, MOPS_E_INVALID, "front/back level counts differ");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = wait_slot(ctx, front))) return rc;
+    if (path && (rc = wait_slot(ctx, back))) return rc;
+
+    const bool host = (cfg->mem == MOPS_MEM_HOST);
+    const long long launches0 = ctx->launches;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev0, st));
+
+    // pathline attributes: only when the front snapshot holds more than one (VK:1093-1104)
+    int attr_count = 0;
+    if (path && F.n_attr_total > 1) attr_count = std::min(std::min(F.n_attr, B.n_attr), MOPS_MAX_ATTRS);
+    const bool want_attr = path && attr_count > 0 && io->out_attr;
+
+    const size_t out_bytes = (size_t)n * each * 3 * sizeof(double);
+    double *d_xyz, *d_out_pos, *d_out_vel, *d_out_attr = nullptr;
+    float* d_depth;
+    int *d_log = nullptr, *d_status = nullptr, *d_steps = nullptr, *d_fcell = nullptr;
+    const int* d_cell0_ext = nullptr;
+    if (host) {
+        if ((rc = ensure(ctx, ctx->p_xyz, (size_t)n * 24))) return rc;
+        if ((rc = ensure(ctx, ctx->p_depth, (size_t)n * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->p_out_pos, out_bytes))) return rc;
+        if ((rc = ensure(ctx, ctx->p_out_vel, out_bytes))) return rc;
+        d_xyz = (double*)ctx->p_xyz.p; d_depth = (float*)ctx->p_depth.p;
+        d_out_pos = (double*)ctx->p_out_pos.p; d_out_vel = (double*)ctx->p_out_vel.p;
+        CK(cudaMemcpyAsync(d_xyz, io->xyz, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_depth, io->depth, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        if (io->cell0) {
+            if ((rc = ensure(ctx, ctx->p_cell0, (size_t)n * 4))) return rc;
+            CK(cudaMemcpyAsync(ctx->p_cell0.p, io->cell0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            d_cell0_ext = (const int*)ctx->p_cell0.p;
+        }
+        if (want_attr) { if ((rc = ensure(ctx, ctx->p_out_attr, out_bytes))) return rc; d_out_attr = (double*)ctx->p_out_attr.p; }
+        if (io->out_cell_log) { if ((rc = ensure(ctx, ctx->p_log, (size_t)n * times * 4))) return rc; d_log = (int*)ctx->p_log.p; }
+        if (io->out_status) { if ((rc = ensure(ctx, ctx->p_status, (size_t)n * 4))) return rc; d_status = (int*)ctx->p_status.p; }
+        if (io->out_steps) { if ((rc = ensure(ctx, ctx->p_steps, (size_t)n * 4))) return rc; d_steps = (int*)ctx->p_steps.p; }
+        if (io->out_cell) { if ((rc = ensure(ctx, ctx->p_fcell, (size_t)n * 4))) return rc; d_fcell = (int*)ctx->p_fcell.p; }
+    } else {
+        d_xyz = io->xyz; d_depth = io->depth; d_out_pos = io->out_pos; d_out_vel = io->out_vel;
+        d_out_attr = want_attr ? io->out_attr : nullptr;
+        d_log = io->out_cell_log; d_status = io->out_status; d_steps = io->out_steps; d_fcell = io->out_cell;
+        d_cell0_ext = io->cell0;
+    }
+    // the reference's output buffers are value-initialised (TrajectoryCommon.h:20-25)
+    CK(cudaMemsetAsync(d_out_pos, 0, out_bytes, st));
+    CK(cudaMemsetAsync(d_out_vel, 0, out_bytes, st));
+    if (d_out_attr) CK(cudaMemsetAsync(d_out_attr, 0, out_bytes, st));
+    if (d_log) CK(cudaMemsetAsync(d_log, 0xff, (size_t)n * times * 4, st));
+
+    // start cells in internal numbering
+    if ((rc = ensure(ctx, ctx->p_cell_int, (size_t)n * 4))) return rc;
+    int* d_cell_int = (int*)ctx->p_cell_int.p;
+    CK(cudaEventRecord(ctx->ev2, st));
+    if (d_cell0_ext) {
+        k_map_ids<<<blocks_for(n, 256), 256, 0, st>>>(d_cell0_ext, d_cell_int, ctx->c_ext2int, ctx->nC, n);
+        ctx->launches++;
+    } else {
+        dispatch_locate(ctx, n, d_xyz, d_cell_int, nullptr);
+    }
+    CK(cudaEventRecord(ctx->ev3, st));
+
+    // processing order: particles sorted by (Morton-numbered) start cell
+    const int* d_order = nullptr;
+    if (cfg->sort_particles && n > 1) {
+        if ((rc = ensure(ctx, ctx->s_vals, (size_t)n * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->s_keys2, (size_t)n * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->s_vals2, (size_t)n * 4))) return rc;
+        k_iota<<<blocks_for(n, 256), 256, 0, st>>>((int*)ctx->s_vals.p, n);
+        ctx->launches++;
+        int bits = 1;
+        while ((1LL << bits) < (long long)ctx->nC + 1 && bits < 31) ++bits;
+        size_t tmp_bytes = 0;
+        // keys are cell ids in [-1, nC): bias by +1 is unnecessary because -1 (invalid) sorts last as unsigned
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned*)d_cell_int, (unsigned*)ctx->s_keys2.p,
+                                        (const int*)ctx->s_vals.p, (int*)ctx->s_vals2.p, (int)n, 0, 32, st);
+        if ((rc = ensure(ctx, ctx->s_tmp, tmp_bytes))) return rc;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->s_tmp.p, tmp_bytes, (const unsigned*)d_cell_int, (unsigned*)ctx->s_keys2.p,
+                                           (const int*)ctx->s_vals.p, (int*)ctx->s_vals2.p, (int)n, 0, 32, st));
+        (void)bits;
+        d_order = (const int*)ctx->s_vals2.p;
+    }
+
+    CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
+    AdvectParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.rec = ctx->rec; P.c4 = ctx->c4; P.c_int2ext = ctx->c_int2ext; P.nC = ctx->nC; P.L = F.L;
+    P.f = view_of(F); P.b = view_of(B);
+    P.attr_count = attr_count;
+    P.use_euler = (cfg->method == MOPS_METHOD_EULER) ? 1 : 0;
+    P.delta_t = (cfg->direction == MOPS_DIR_FORWARD ? 1 : -1) * (int)cfg->delta_t;
+    P.times = times; P.each = each; P.record_t = (int)cfg->record_t;
+    P.record_interval = (int)(cfg->record_t / cfg->delta_t);
+    P.duration = (double)cfg->duration;
+    P.n = n; P.order = d_order;
+    P.pos = d_xyz; P.depth = d_depth; P.cell0 = d_cell_int;
+    P.out_pos = d_out_pos; P.out_vel = d_out_vel; P.out_attr = d_out_attr;
+    P.cell_log = d_log; P.status = d_status; P.steps = d_steps; P.fcell = d_fcell;
+    P.counters = ctx->counters;
+
+    CK(cudaEventRecord(ctx->ev1, st));
+    switch (ctx->M) {
+    case 6: launch_advect<6>(ctx, P, path); break;
+    case 8: launch_advect<8>(ctx, P, path); break;
+    default: launch_advect<20>(ctx, P, path); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_kend, st));
+    if ((rc = mark_use(ctx, front))) return rc;
+    if (path && back != front && (rc = mark_use(ctx, back))) return rc;
+
+    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    if (host) {
+        CK(cudaMemcpyAsync(io->xyz, d_xyz, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(io->depth, d_depth, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(io->out_pos, d_out_pos, out_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(io->out_vel, d_out_vel, out_bytes, cudaMemcpyDeviceToHost, st));
+        if (d_out_attr) CK(cudaMemcpyAsync(io->out_attr, d_out_attr, out_bytes, cudaMemcpyDeviceToHost, st));
+        if (d_log) CK(cudaMemcpyAsync(io->out_cell_log, d_log, (size_t)n * times * 4, cudaMemcpyDeviceToHost, st));
+        if (d_status) CK(cudaMemcpyAsync(io->out_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (d_steps) CK(cudaMemcpyAsync(io->out_steps, d_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (d_fcell) CK(cudaMemcpyAsync(io->out_cell, d_fcell, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    // host-memory calls complete before returning; device-memory calls stay asynchronous on the
+    // context's stream unless the caller asks for stats
+    if (host || stats) {
+        CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_end, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->particle_steps = (int64_t)h_counters[0];
+        stats->alive_at_end = (int64_t)h_counters[1];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev_kend) == cudaSuccess) stats->kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) stats->locate_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_end) == cudaSuccess) stats->total_ms = ms;
+        stats->launches = (int32_t)(ctx->launches - launches0);
+    }
+    return MOPS_OK;
+}
+
+template <int M>
+void launch_remap(mops_ctx* ctx, const RemapParams& P)
+{
+    k_remap<M><<<blocks_for((long long)P.width * P.height, 128), 128, 0, ctx->stream>>>(P);
+    ctx->launches++;
+}
+
+} // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int mops_abi_version(void) { return MOPS_B200_ABI_VERSION; }
+
+int mops_create(mops_ctx** out, int device_ordinal)
+{
+    if (!out) return MOPS_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MOPS_E_NODEVICE;
+    if (device_ordinal < 0 || device_ordinal >= ndev) return MOPS_E_NODEVICE;
+    mops_ctx* ctx = new mops_ctx();
+    ctx->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device_ordinal) != cudaSuccess) {
+        delete ctx;
+        return MOPS_E_NODEVICE;
+    }
+    // the kernels are built for sm_100a only: refuse anything else loudly
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, (const void*)k_iota) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return MOPS_E_NODEVICE;
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_kend) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess &&
+              cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess;
+    for (int i = 0; ok && i < MOPS_MAX_SNAPSHOT_SLOTS; ++i) {
+        ok = cudaEventCreate(&ctx->snap[i].ready) == cudaSuccess && cudaEventCreate(&ctx->snap[i].last_use) == cudaSuccess;
+    }
+    if (!ok) {
+        delete ctx;
+        return MOPS_E_CUDA;
+    }
+    *out = ctx;
+    return MOPS_OK;
+}
+
+void mops_destroy(mops_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_mesh(ctx);
+    for (auto& s : ctx->snap) {
+        free_snapshot(s);
+        if (s.ready) cudaEventDestroy(s.ready);
+        if (s.last_use) cudaEventDestroy(s.last_use);
+    }
+    Buf* bufs[] = {&ctx->st_zonal, &ctx->st_merid, &ctx->st_thick, &ctx->st_wtop, &ctx->st_bottom, &ctx->st_ztopc, &ctx->st_attr,
+                   &ctx->st_vmono, &ctx->p_xyz, &ctx->p_depth, &ctx->p_cell0, &ctx->p_cell_int, &ctx->p_out_pos, &ctx->p_out_vel,
+                   &ctx->p_out_attr, &ctx->p_log, &ctx->p_status, &ctx->p_steps, &ctx->p_fcell, &ctx->s_keys, &ctx->s_vals,
+                   &ctx->s_keys2, &ctx->s_vals2, &ctx->s_tmp, &ctx->r_img0, &ctx->r_img1, &ctx->r_cells};
+    for (Buf* b : bufs) cudaFree(b->p);
+    cudaFree(ctx->counters);
+    cudaFree(ctx->d_nonmono);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+    cudaEventDestroy(ctx->ev_kend); cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->side);
+    delete ctx;
+}
+
+const char* mops_last_error(const mops_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mops_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return MOPS_E_INVALID;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? MOPS_OK : MOPS_E_NOMEM;
+}
+
+int mops_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MOPS_OK : MOPS_E_CUDA; }
+
+int mops_synchronize(mops_ctx* ctx)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->side));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MOPS_OK;
+}
+
+int mops_set_mesh(mops_ctx* ctx, int32_t n_cells, int32_t n_vertices, int32_t max_edges, const double* cell_xyz,
+                  const double* vertex_xyz, const int32_t* vertices_on_cell, const int32_t* cells_on_cell,
+                  const int32_t* cells_on_vertex, const int32_t* n_edges_on_cell)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (n_cells <= 0 || n_vertices <= 0 || max_edges <= 0) return fail(ctx, MOPS_E_INVALID, "bad mesh sizes");
+    if (!cell_xyz || !vertex_xyz || !vertices_on_cell || !cells_on_cell || !cells_on_vertex || !n_edges_on_cell)
+        return fail(ctx, MOPS_E_INVALID, "null mesh array");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    free_mesh(ctx);
+    for (auto& s : ctx->snap) free_snapshot(s);
+    ctx->nC = n_cells; ctx->nV = n_vertices; ctx->maxEdges = max_edges;
+    const size_t nC = (size_t)n_cells, nV = (size_t)n_vertices;
+
+    int max_nv = 0;
+    for (size_t c = 0; c < nC; ++c) max_nv = std::max(max_nv, (int)n_edges_on_cell[c]);
+    max_nv = std::min(max_nv, (int)max_edges);
+    // reference: more than MAX_VERTEX_NUM = 20 vertices makes every evaluation fail (VK:741-751)
+    ctx->M = (max_nv <= 6) ? 6 : (max_nv <= 8) ? 8 : 20;
+
+    // Morton renumbering of cells and vertices (layout only; ids crossing the ABI stay the caller's)
+    std::vector<int> c_int2ext, v_int2ext, c_ext2int(nC), v_ext2int(nV);
+    morton_order(cell_xyz, n_cells, c_int2ext);
+    morton_order(vertex_xyz, n_vertices, v_int2ext);
+    for (size_t i = 0; i < nC; ++i) c_ext2int[c_int2ext[i]] = (int)i;
+    for (size_t i = 0; i < nV; ++i) v_ext2int[v_int2ext[i]] = (int)i;
+
+    double rsum = 0.0;
+    const size_t rs = std::min<size_t>(nC, 64);
+    for (size_t i = 0; i < rs; ++i)
+        rsum += std::sqrt(cell_xyz[3 * i] * cell_xyz[3 * i] + cell_xyz[3 * i + 1] * cell_xyz[3 * i + 1] + cell_xyz[3 * i + 2] * cell_xyz[3 * i + 2]);
+    ctx->radius = rsum / (double)rs;
+
+    int rc = MOPS_OK;
+    switch (ctx->M) {
+    case 6: rc = upload_records<6>(ctx, vertex_xyz, vertices_on_cell, cells_on_cell, n_edges_on_cell, c_int2ext, c_ext2int, v_ext2int); break;
+    case 8: rc = upload_records<8>(ctx, vertex_xyz, vertices_on_cell, cells_on_cell, n_edges_on_cell, c_int2ext, c_ext2int, v_ext2int); break;
+    default: rc = upload_records<20>(ctx, vertex_xyz, vertices_on_cell, cells_on_cell, n_edges_on_cell, c_int2ext, c_ext2int, v_ext2int); break;
+    }
+    if (rc) { free_mesh(ctx); return rc; }
+
+    // cell centres (internal order, one 32 B sector each), id maps
+    std::vector<double4> h_c4(nC);
+    for (size_t i = 0; i < nC; ++i) {
+        const size_t e = (size_t)c_int2ext[i];
+        h_c4[i] = make_double4(cell_xyz[3 * e], cell_xyz[3 * e + 1], cell_xyz[3 * e + 2], 0.0);
+    }
+    std::vector<VertRec> h_vert(nV);
+    std::vector<int> h_vcell(nV * 3);
+    for (size_t i = 0; i < nV; ++i) {
+        const size_t ve = (size_t)v_int2ext[i];
+        VertRec r;
+        std::memset(&r, 0, sizeof(r));
+        int ids[3];
+        for (int t = 0; t < 3; ++t) {
+            // reference boundary test: (cellsOnVertex - 1 as size_t) > nCells + 1  (ST:33-40); ids in
+            // (nCells-1, nCells+1] would index out of range in the reference -- treated as boundary here
+            const long long e = (long long)cells_on_vertex[3 * ve + t] - 1;
+            if (e < 0 || e >= (long long)n_cells) { r.boundary = 1; ids[t] = 0; }
+            else ids[t] = (int)e;
+            h_vcell[3 * i + t] = ids[t];
+        }
+        r.c0 = c_ext2int[ids[0]]; r.c1 = c_ext2int[ids[1]]; r.c2 = c_ext2int[ids[2]];
+        h_vert[i] = r;
+    }
+    double *d_cell_ext = nullptr, *d_vert_ext = nullptr;
+    CK(cudaMalloc(&ctx->c4, nC * sizeof(double4)));
+    CK(cudaMalloc(&ctx->trig, nC * sizeof(double4)));
+    CK(cudaMalloc(&ctx->vert, nV * sizeof(VertRec)));
+    CK(cudaMalloc(&ctx->vcell_ext, nV * 3 * sizeof(int)));
+    CK(cudaMalloc(&ctx->c_int2ext, nC * sizeof(int)));
+    CK(cudaMalloc(&ctx->c_ext2int, nC * sizeof(int)));
+    CK(cudaMalloc(&ctx->v_int2ext, nV * sizeof(int)));
+    CK(cudaMalloc(&ctx->v_ext2int, nV * sizeof(int)));
+    CK(cudaMalloc(&d_cell_ext, nC * 24));
+    CK(cudaMalloc(&d_vert_ext, nV * 24));
+    ctx->mesh_bytes += nC * (2 * sizeof(double4) + 8) + nV * (sizeof(VertRec) + 12 + 8);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->c4, h_c4.data(), nC * sizeof(double4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->vert, h_vert.data(), nV * sizeof(VertRec), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->vcell_ext, h_vcell.data(), nV * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->c_int2ext, c_int2ext.data(), nC * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->c_ext2int, c_ext2int.data(), nC * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->v_int2ext, v_int2ext.data(), nV * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->v_ext2int, v_ext2int.data(), nV * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cell_ext, cell_xyz, nC * 24, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_vert_ext, vertex_xyz, nV * 24, cudaMemcpyHostToDevice, st));
+    k_cell_trig<<<blocks_for(n_cells, 256), 256, 0, st>>>(d_cell_ext, ctx->trig, n_cells);
+    k_vert_bary<<<blocks_for(n_vertices, 256), 256, 0, st>>>(ctx->vert, ctx->v_int2ext, d_vert_ext, d_cell_ext, ctx->vcell_ext, n_vertices);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    switch (ctx->M) {
+    case 6: rc = build_cube<6>(ctx); break;
+    case 8: rc = build_cube<8>(ctx); break;
+    default: rc = build_cube<20>(ctx); break;
+    }
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_cell_ext));
+    CK(cudaFree(d_vert_ext));
+
+    // keep the mesh records resident in L2 where the device allows it (access-policy window on
+    // both streams; hitRatio scaled when the records exceed the persisting carve-out)
+    if (ctx->prop.persistingL2CacheMaxSize > 0 && ctx->prop.accessPolicyMaxWindowSize > 0) {
+        const size_t rec_bytes = (ctx->M == 6 ? sizeof(CellRec<6>) : ctx->M == 8 ? sizeof(CellRec<8>) : sizeof(CellRec<20>)) * nC;
+        const size_t carve = std::min<size_t>((size_t)ctx->prop.persistingL2CacheMaxSize, rec_bytes);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            std::memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = ctx->rec;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(rec_bytes, (size_t)ctx->prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError();
+    }
+    ctx->has_mesh = true;
+    return MOPS_OK;
+}
+
+int mops_set_snapshot(mops_ctx* ctx, int32_t slot, int32_t n_levels, const double* zonal, const double* meridional,
+                      const double* layer_thickness, const double* bottom_depth, const double* vert_vel_top, int32_t n_attr,
+                      const double* const* attrs, int32_t n_attr_total)
+{
+    return set_snapshot_impl(ctx, slot, n_levels, zonal, meridional, layer_thickness, bottom_depth, vert_vel_top, n_attr, attrs,
+                             n_attr_total, false);
+}
+
+int mops_set_snapshot_async(mops_ctx* ctx, int32_t slot, int32_t n_levels, const double* zonal, const double* meridional,
+                            const double* layer_thickness, const double* bottom_depth, const double* vert_vel_top, int32_t n_attr,
+                            const double* const* attrs, int32_t n_attr_total)
+{
+    return set_snapshot_impl(ctx, slot, n_levels, zonal, meridional, layer_thickness, bottom_depth, vert_vel_top, n_attr, attrs,
+                             n_attr_total, true);
+}
+
+int mops_snapshot_wait(mops_ctx* ctx, int32_t slot)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (slot < 0 || slot >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[slot].valid) return fail(ctx, MOPS_E_STATE, "slot %d not set", slot);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->snap[slot].ready));
+    return MOPS_OK;
+}
+
+int mops_get_prepared(mops_ctx* ctx, int32_t slot, double* ztop_vertex, double* vel_vertex, double* vertvel_vertex,
+                      double* attr0_vertex, double* attr1_vertex)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (slot < 0 || slot >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[slot].valid) return fail(ctx, MOPS_E_STATE, "slot %d not set", slot);
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = wait_slot(ctx, slot))) return rc;
+    Snapshot& s = ctx->snap[slot];
+    const size_t nV = (size_t)ctx->nV, L = (size_t)s.L;
+    double *d_z = nullptr, *d_v = nullptr, *d_w = nullptr, *d_a0 = nullptr, *d_a1 = nullptr;
+    if (ztop_vertex) CK(cudaMalloc(&d_z, nV * L * 8));
+    if (vel_vertex) CK(cudaMalloc(&d_v, nV * L * 24));
+    if (vertvel_vertex) CK(cudaMalloc(&d_w, nV * (L + 1) * 8));
+    if (attr0_vertex && s.attr[0]) CK(cudaMalloc(&d_a0, nV * L * 8));
+    if (attr1_vertex && s.attr[1]) CK(cudaMalloc(&d_a1, nV * L * 8));
+    k_export_prepared<<<blocks_for((long long)nV * L, 256), 256, 0, ctx->stream>>>(ctx->v_ext2int, s.ztop, s.velw, s.attr[0], s.attr[1],
+                                                                                 d_z, d_v, d_w, d_a0, d_a1, ctx->nV, s.L);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (d_z) CK(cudaMemcpyAsync(ztop_vertex, d_z, nV * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_v) CK(cudaMemcpyAsync(vel_vertex, d_v, nV * L * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_w) CK(cudaMemcpyAsync(vertvel_vertex, d_w, nV * (L + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_a0) CK(cudaMemcpyAsync(attr0_vertex, d_a0, nV * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_a1) CK(cudaMemcpyAsync(attr1_vertex, d_a1, nV * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_z); cudaFree(d_v); cudaFree(d_w); cudaFree(d_a0); cudaFree(d_a1);
+    return MOPS_OK;
+}
+
+int mops_locate(mops_ctx* ctx, int32_t mem, int64_t n, const double* xyz, int32_t* cell_out)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "no mesh");
+    if (n < 0 || (n > 0 && (!xyz || !cell_out))) return fail(ctx, MOPS_E_INVALID, "bad locate arguments");
+    if (n == 0) return MOPS_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (mem == MOPS_MEM_HOST) {
+        if ((rc = ensure(ctx, ctx->p_xyz, (size_t)n * 24))) return rc;
+        if ((rc = ensure(ctx, ctx->p_cell0, (size_t)n * 4))) return rc;
+        CK(cudaMemcpyAsync(ctx->p_xyz.p, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+        dispatch_locate(ctx, n, (const double*)ctx->p_xyz.p, nullptr, (int*)ctx->p_cell0.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cell_out, ctx->p_cell0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        dispatch_locate(ctx, n, xyz, nullptr, cell_out);
+        CK(cudaGetLastError());
+    }
+    return MOPS_OK;
+}
+
+int mops_streamline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io, mops_traj_stats* stats)
+{
+    return trajectory_impl(ctx, cfg, slot, slot, io, stats, false);
+}
+
+int mops_pathline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot, const mops_traj_io* io,
+                  mops_traj_stats* stats)
+{
+    return trajectory_impl(ctx, cfg, front_slot, back_slot, io, stats, true);
+}
+
+int mops_remap_fixed_depth(mops_ctx* ctx, const mops_remap_cfg* cfg, int32_t slot, double* img0, double* img1, int32_t* pixel_cell,
+                           mops_remap_stats* stats)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (!cfg || !img0) return fail(ctx, MOPS_E_INVALID, "null cfg/img0");
+    if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "no mesh");
+    if (slot < 0 || slot >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[slot].valid) return fail(ctx, MOPS_E_STATE, "snapshot slot %d not set", slot);
+    if (cfg->width <= 0 || cfg->height <= 0) return fail(ctx, MOPS_E_INVALID, "bad image size");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = wait_slot(ctx, slot))) return rc;
+    Snapshot& S = ctx->snap[slot];
+    const size_t npx = (size_t)cfg->width * cfg->height;
+    const bool host = (cfg->mem == MOPS_MEM_HOST);
+    const bool attr_image = (S.n_attr_total > 1) && img1; // VK:259-267
+    const long long launches0 = ctx->launches;
+    cudaStream_t st = ctx->stream;
+    double *d0, *d1 = nullptr;
+    int* dc = nullptr;
+    CK(cudaEventRecord(ctx->ev0, st));
+    if (host) {
+        if ((rc = ensure(ctx, ctx->r_img0, npx * 32))) return rc;
+        d0 = (double*)ctx->r_img0.p;
+        if (attr_image) { if ((rc = ensure(ctx, ctx->r_img1, npx * 32))) return rc; d1 = (double*)ctx->r_img1.p; }
+        if (pixel_cell) { if ((rc = ensure(ctx, ctx->r_cells, npx * 4))) return rc; dc = (int*)ctx->r_cells.p; }
+    } else {
+        d0 = img0; d1 = attr_image ? img1 : nullptr; dc = pixel_cell;
+    }
+    CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
+    RemapParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.rec = ctx->rec; P.c4 = ctx->c4; P.cube = ctx->cube; P.c_int2ext = ctx->c_int2ext; P.F = ctx->F; P.nC = ctx->nC; P.L = S.L;
+    P.s = view_of(S);
+    P.attr_count = S.n_attr; P.attr_image = attr_image ? 1 : 0;
+    P.width = cfg->width; P.height = cfg->height;
+    P.minLat = cfg->lat_min; P.maxLat = cfg->lat_max; P.minLon = cfg->lon_min; P.maxLon = cfg->lon_max;
+    P.DEPTH = -cfg->fixed_depth;
+    P.img0 = d0; P.img1 = d1; P.pixel_cell = dc; P.nan_count = ctx->counters + 2;
+    CK(cudaEventRecord(ctx->ev1, st));
+    switch (ctx->M) {
+    case 6: launch_remap<6>(ctx, P); break;
+    case 8: launch_remap<8>(ctx, P); break;
+    default: launch_remap<20>(ctx, P); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev2, st));
+    if ((rc = mark_use(ctx, slot))) return rc;
+    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    if (host) {
+        CK(cudaMemcpyAsync(img0, d0, npx * 32, cudaMemcpyDeviceToHost, st));
+        if (d1) CK(cudaMemcpyAsync(img1, d1, npx * 32, cudaMemcpyDeviceToHost, st));
+        if (dc) CK(cudaMemcpyAsync(pixel_cell, dc, npx * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (host || stats) {
+        CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev3, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2) == cudaSuccess) stats->kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3) == cudaSuccess) stats->total_ms = ms;
+        stats->nan_pixels = (int64_t)h_counters[2];
+        stats->launches = (int32_t)(ctx->launches - launches0);
+        stats->n_images = attr_image ? 2 : 1;
+    }
+    return MOPS_OK;
+}
+
+// Line assembly + NaN trimming exactly as the reference's host code does it
+// (InitTrajectoryLines / FinalizeTrajectoryLines[WithAttrs] / RemoveNaNTrajectoriesAndReindex,
+// src/Common/TrajectoryCommon.h:43-190; pinned by the reference's test/test_trajector.cpp).
+int mops_finalize_lines(int64_t n, int32_t each, const double* seeds, const double* raw_pos, const double* raw_vel,
+                        int32_t pathline_mode, double* points, double* velocity, double* temperature, double* salinity,
+                        double* last)
+{
+    if (n < 0 || each <= 0 || (n > 0 && (!seeds || !raw_pos || !raw_vel || !points || !velocity))) return MOPS_E_INVALID;
+    const int64_t per = (int64_t)each + 1;
+    auto finite = [](const double* p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); };
+    for (int64_t i = 0; i < n; ++i) {
+        double* P = points + i * per * 3;
+        double* V = velocity + i * per * 3;
+        double* T = temperature ? temperature + i * per : nullptr;
+        double* S = salinity ? salinity + i * per : nullptr;
+        // points = [seed, rec_0 .. rec_each-1]; velocity = [vel_0 .. vel_each-1, 0] (one shorter, zero padded)
+        std::memcpy(P, seeds + 3 * i, 24);
+        std::memcpy(P + 3, raw_pos + i * each * 3, (size_t)each * 24);
+        std::memcpy(V, raw_vel + i * each * 3, (size_t)each * 24);
+        V[3 * each] = V[3 * each + 1] = V[3 * each + 2] = 0.0;
+        for (int64_t k = 0; k < per; ++k) {
+            // FinalizeTrajectoryLinesWithAttrs pushes velocity.x / velocity.y, not the attributes (:179-180)
+            const bool src = pathline_mode && k < each;
+            if (T) T[k] = src ? raw_vel[(i * each + k) * 3] : 0.0;
+            if (S) S[k] = src ? raw_vel[(i * each + k) * 3 + 1] : 0.0;
+        }
+        int64_t cut = 0;
+        for (; cut < per; ++cut)
+            if (!finite(P + 3 * cut)) break;
+        if (cut == 0) {
+            const double ft = T ? T[0] : 0.0, fs = S ? S[0] : 0.0;
+            for (int64_t j = 0; j < per; ++j) {
+                std::memcpy(P + 3 * j, P, 24);
+                V[3 * j] = V[3 * j + 1] = V[3 * j + 2] = 0.0;
+                if (T) T[j] = ft;
+                if (S) S[j] = fs;
+            }
+        } else if (cut < per) {
+            const double lt = T ? T[cut - 1] : 0.0, ls = S ? S[cut - 1] : 0.0;
+            V[3 * (cut - 1)] = V[3 * (cut - 1) + 1] = V[3 * (cut - 1) + 2] = 0.0;
+            for (int64_t j = cut; j < per; ++j) {
+                std::memcpy(P + 3 * j, P + 3 * (cut - 1), 24);
+                V[3 * j] = V[3 * j + 1] = V[3 * j + 2] = 0.0;
+                if (T) T[j] = lt;
+                if (S) S[j] = ls;
+            }
+        }
+        if (last) std::memcpy(last + 3 * i, P + 3 * (per - 1), 24);
+    }
+    return MOPS_OK;
+}
+
+int mops_get_info(mops_ctx* ctx, mops_info* out)
+{
+    if (!ctx || !out) return MOPS_E_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    out->device = ctx->device;
+    out->sm_count = ctx->prop.multiProcessorCount;
+    out->cc_major = ctx->prop.major;
+    out->cc_minor = ctx->prop.minor;
+    out->l2_bytes = ctx->prop.l2CacheSize;
+    out->hbm_bytes = (int64_t)ctx->prop.totalGlobalMem;
+    out->mesh_bytes = (int64_t)ctx->mesh_bytes;
+    for (int i = 0; i < MOPS_MAX_SNAPSHOT_SLOTS; ++i) {
+        out->snapshot_bytes[i] = (int64_t)ctx->snap[i].bytes;
+        if (ctx->snap[i].valid && ctx->snap[i].nonmono < 0 && cudaEventQuery(ctx->snap[i].ready) == cudaSuccess) {
+            // async upload: fetch the count lazily once its preprocessing has completed
+            cudaMemcpy(&ctx->snap[i].nonmono, ctx->d_nonmono + i, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        out->nonmonotone_cells[i] = ctx->snap[i].nonmono;
+        if (ctx->snap[i].valid) out->n_levels = ctx->snap[i].L;
+    }
+    out->record_width = ctx->M;
+    out->total_launches = ctx->launches;
+    return MOPS_OK;
+}
+
+} // extern "C"

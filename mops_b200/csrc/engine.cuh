@@ -1,0 +1,541 @@
+// engine.cuh -- device-side data layout and the per-point evaluation shared by the
+// streamline / pathline / remap kernels.
+//
+// Reference being re-designed (paths relative to the reference root; VK =
+// src/CPU/TBB/Kernel/MPASOVisualizerKernels.cpp, TK = src/CPU/TBB/Kernel/TBBKernel.h):
+//   calc_velocity_at (streamline) VK:740-872, (pathline) VK:1124-1327, remap pixel VK:288-470,
+//   IsInMesh TK:21-54, CalcPolygonWachspress src/Utils/Interpolation.hpp:137-165,
+//   CalcVelocity / CalcAttribute TK:128-164.
+//
+// What is different from the reference (and why results are still identical):
+//  * one packed, 32-byte-aligned record per cell (CellRec) holds everything a particle
+//    needs from the mesh: vertex ids, neighbour ids, vertex positions, and two
+//    point-independent products the reference recomputes for every evaluation -- the edge
+//    normals cross(v_k, v_k+1) of IsInMesh and the Wachspress corner areas B_i.  They are
+//    computed once per mesh by the same expressions, so every later result is bit-equal.
+//  * the depth column is never materialised (the reference keeps double[100] per thread):
+//    when every vertex column of the cell is non-increasing (checked once per snapshot)
+//    the interpolated column is non-increasing too (weights are >= 0, rounding is
+//    monotone), the reference's fix-up `z[k] = z[k-1] - 1e-9` is a no-op, and the layer
+//    search may probe levels on the fly.  A layer hint from the previous evaluation is
+//    accepted only when it is provably the unique answer of the reference's search;
+//    otherwise the reference's search runs.  Cells that fail the check take a streaming
+//    restatement of the full-column path.
+//  * velocity (x,y,z) and vertical velocity share one 32-byte (vertex, level) record.
+#pragma once
+#include "dmath.cuh"
+#include <stdint.h>
+
+namespace mops {
+
+// ---- resident mesh ----------------------------------------------------------------------
+template <int M>
+struct alignas(32) CellRec {
+    int nv;       // nEdgesOnCell; 0 when the cell is unusable (nv > M cannot happen by construction)
+    int pad;
+    int vid[M];   // internal vertex ids (0-based), -1 beyond nv
+    int nbr[M];   // internal neighbour cell ids in cellsOnCell order, -1 = none
+    double vx[M], vy[M], vz[M]; // vertex positions
+    double nx[M], ny[M], nz[M]; // cross(v_k, v_(k+1)%nv)                      (TK:45)
+    double B[M];                // triangle_area(v_(i-1), v_i, v_(i+1))       (Interpolation.hpp:154)
+};
+
+struct VertRec {      // per Voronoi vertex, mesh-constant part of the cell->vertex interpolation
+    int c0, c1, c2;   // internal ids of cellsOnVertex
+    int boundary;     // reference's `(id-1) > nCells+1` test (MPASOSolutionTBB.cpp:35)
+    double u, v, w;   // calcTriangleBarycentric of the vertex in (c0,c1,c2) (Interpolation.hpp:79-93)
+};
+
+struct SnapView {
+    const double* __restrict__ ztop;        // [nV][L]   cellVertexZTop, internal vertex order
+    const double4* __restrict__ velw;       // [nV][L]   (vx,vy,vz, vertVelocityTop level k)
+    const double* __restrict__ attr0;       // [nV][L] or null
+    const double* __restrict__ attr1;
+    const unsigned char* __restrict__ mono; // [nC] 1 = all vertex columns of the cell non-increasing
+};
+
+enum {
+    ST_ALIVE = 0, ST_BAD_CELL = 1, ST_NOT_IN_CELL = 2, ST_BAD_COLUMN = 3, ST_ZERO_VELOCITY = 4,
+    ST_ABOVE_SURFACE = 5, ST_BAD_SETUP = 6
+};
+
+// ---- Wachspress weights + in-cell test ------------------------------------------------
+// returns false when the point is not in the cell (IsInMesh).  w[] are the normalised
+// weights, vo[i] = vid[i]*L (row offsets into the vertex-major arrays); wfinite tells
+// whether all weights are finite (a point exactly on an edge gives inf/NaN, Appendix B N7).
+template <int M>
+__device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
+                                             double (&w)[M], bool& wfinite)
+{
+    if (!finite3(px, py, pz)) return false; // TK:29-33
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        if (k < nv) {
+            const double direction = rec->nx[k] * px + rec->ny[k] * py + rec->nz[k] * pz; // TK:46
+            if (direction < 0.0) inside = false;
+        }
+    }
+    if (!inside) return false;
+
+    double ax[M], ay[M], az[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        ax[k] = rec->vx[k]; ay[k] = rec->vy[k]; az[k] = rec->vz[k];
+    }
+    double ar[M]; // ar[k] = area(v_k, v_(k+1)%nv, p)
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        if (k < nv) {
+            const bool wrap = (k + 1 >= nv);
+            const double bx = wrap ? ax[0] : ax[(k + 1) % M];
+            const double by = wrap ? ay[0] : ay[(k + 1) % M];
+            const double bz = wrap ? az[0] : az[(k + 1) % M];
+            ar[k] = tri_area(ax[k], ay[k], az[k], bx, by, bz, px, py, pz);
+        } else {
+            ar[k] = 0.0;
+        }
+    }
+    double prev = ar[0]; // A_i of i = 0 is area(v_(nv-1), v_0, p) = ar[nv-1]
+#pragma unroll
+    for (int k = 1; k < M; ++k)
+        if (k == nv - 1) prev = ar[k];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        if (i < nv) {
+            w[i] = rec->B[i] / (prev * ar[i]);
+            sum += w[i];
+            prev = ar[i];
+        } else {
+            w[i] = 0.0;
+        }
+    }
+    const double recp = 1.0 / sum;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+        if (i < nv) w[i] *= recp;
+    wfinite = isfinite(sum) && isfinite(recp) && (sum > 0.0);
+    return true;
+}
+
+// ---- interpolated zTop column ---------------------------------------------------------------
+struct LayerRes {
+    int layer;       // reference's local_layer; for the pathline 0 = above surface, -1 = none
+    double top, bot; // z[layer-1], z[layer] (after the fix-up)
+};
+
+// FAST PATH: the column is provably non-increasing, so raw value == fixed-up value and levels
+// are probed on the fly with the weights / row offsets held in registers.
+template <int M>
+struct ZCol {
+    const double* __restrict__ ztop;
+    const double (&w)[M];
+    const int (&vo)[M];
+    int nv;
+    int L;
+    __device__ __forceinline__ double operator()(int k) const
+    {
+        double z = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+            if (i < nv) z += w[i] * ztop[vo[i] + k]; // VK:774-781, accumulated in vertex order
+        return z;
+    }
+};
+
+// SLOW PATH (cells with a non-monotone vertex column, or non-finite weights): the reference's
+// full column with its prefix-dependent fix-up (VK:772-789), materialised in a local array
+// inside a non-inlined function so that the fast path keeps its arrays in registers.
+template <int M>
+struct ColArgs {
+    const double* ztop;
+    double w[M];
+    int vo[M];
+    int nv, L;
+};
+
+template <int M>
+__device__ __forceinline__ ColArgs<M> make_col_args(const double* ztop, const double (&w)[M], const int (&vo)[M], int nv, int L)
+{
+    ColArgs<M> a;
+    a.ztop = ztop; a.nv = nv; a.L = L;
+#pragma unroll
+    for (int i = 0; i < M; ++i) { a.w[i] = w[i]; a.vo[i] = vo[i]; }
+    return a;
+}
+
+template <int M>
+__device__ __forceinline__ void fill_fixed_column(const ColArgs<M>& a, double* col)
+{
+    for (int k = 0; k < a.L; ++k) {
+        double z = 0.0;
+        for (int i = 0; i < a.nv; ++i) z += a.w[i] * a.ztop[a.vo[i] + k];
+        col[k] = z;
+    }
+    for (int k = 1; k < a.L; ++k)
+        if (col[k] > col[k - 1]) col[k] = col[k - 1] - 1e-9;
+}
+
+// streamline layer search, VK:791-822 (binary, eps = 1e-8) on any column accessor
+template <class Z>
+__device__ __forceinline__ LayerRes binary_layer_search(const Z& z, int L, double d)
+{
+    const double eps = 1e-8;
+    int layer;
+    if (d > z(0) + eps) {
+        layer = 1;
+    } else if (d < z(L - 1) - eps) {
+        layer = L - 1;
+    } else {
+        int lo = 1, hi = L - 1, ans = 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const double top_i = z(mid - 1);
+            const double bot_i = z(mid);
+            if (d <= top_i + eps && d >= bot_i - eps) {
+                ans = mid;
+                break;
+            }
+            if (d > top_i + eps) hi = mid - 1;
+            else lo = mid + 1;
+        }
+        if (ans < 1) ans = 1;
+        if (ans > L - 1) ans = L - 1;
+        layer = ans;
+    }
+    LayerRes r;
+    r.layer = layer;
+    r.top = z(layer - 1);
+    r.bot = z(layer);
+    return r;
+}
+
+struct ArrayCol {
+    const double* col;
+    __device__ __forceinline__ double operator()(int k) const { return col[k]; }
+};
+
+template <int M>
+__device__ __noinline__ LayerRes slow_layer_stream(const ColArgs<M> a, double d)
+{
+    double col[100];
+    fill_fixed_column<M>(a, col);
+    return binary_layer_search(ArrayCol{col}, a.L, d);
+}
+
+// `hint` (a previous answer, or < 1) is accepted only if it is the unique matching layer, in
+// which case the reference's search returns it as well (proof in DESIGN.md, "layer hint").
+template <int M>
+__device__ __forceinline__ LayerRes layer_search_stream(const ZCol<M>& z, double d, int hint)
+{
+    const double eps = 1e-8;
+    const int L = z.L;
+    if (hint >= 1 && hint <= L - 1) {
+        LayerRes r;
+        r.layer = hint;
+        r.top = z(hint - 1);
+        r.bot = z(hint);
+        if (d <= r.top + eps && d >= r.bot - eps && d > r.bot + eps && d < r.top - eps) return r;
+    }
+    return binary_layer_search(z, L, d);
+}
+
+// pathline layer search, VK:1182-1218: above surface -> 0 (caller reports ABOVE_SURFACE),
+// below bottom -> L-1, else the FIRST k in 1..L-1 with d <= z[k-1]+eps && d >= z[k]-eps.
+template <int M>
+__device__ __noinline__ LayerRes slow_layer_path(const ColArgs<M> a, double d)
+{
+    double col[100];
+    fill_fixed_column<M>(a, col);
+    const double eps = 1e-8;
+    const int L = a.L;
+    LayerRes r;
+    r.layer = -1; r.top = 0.0; r.bot = 0.0;
+    if (d > col[0] + eps) { r.layer = 0; return r; }
+    if (d < col[L - 1] - eps) {
+        r.layer = L - 1;
+    } else {
+        for (int k = 1; k < L; ++k)
+            if (d <= col[k - 1] + eps && d >= col[k] - eps) { r.layer = k; break; }
+    }
+    if (r.layer >= 1) { r.top = col[r.layer - 1]; r.bot = col[r.layer]; }
+    return r;
+}
+
+// remap (VisualizeFixedDepth) column logic on the fixed-up column, VK:346-409.  layer = -2: depth
+// outside [z_bot - epsd, z_surf + epsd]; -1: no layer; else local_layer with top = z[max(0,l-1)].
+template <int M>
+__device__ __noinline__ LayerRes slow_layer_remap(const ColArgs<M> a, double DEPTH)
+{
+    double col[100];
+    fill_fixed_column<M>(a, col);
+    const int L = a.L;
+    LayerRes r;
+    r.layer = -1; r.top = 0.0; r.bot = 0.0;
+    double z_surf = col[0], z_bot = col[L - 1];
+    if (z_surf < z_bot) { const double t = z_surf; z_surf = z_bot; z_bot = t; }
+    const double ad = 1e-8 * fabs(z_surf - z_bot);
+    const double epsd = (1e-6 < ad) ? ad : 1e-6;
+    if (!(DEPTH <= z_surf + epsd && DEPTH >= z_bot - epsd)) { r.layer = -2; return r; }
+    for (int k = 1; k < L; ++k) {
+        double tI = col[k - 1], bI = col[k];
+        if (tI < bI) { const double t = tI; tI = bI; bI = t; }
+        if (DEPTH <= tI + 1e-8 && DEPTH >= bI - 1e-8) { r.layer = k; break; }
+    }
+    if (DEPTH <= col[0]) r.layer = 0;
+    if (r.layer < 0) return r;
+    r.top = col[(r.layer - 1 > 0) ? r.layer - 1 : 0];
+    r.bot = col[r.layer];
+    return r;
+}
+
+// On a non-increasing column the first match is the smallest k with d >= z[k]-eps (lower bound).
+template <int M>
+__device__ __forceinline__ LayerRes layer_search_path(const ZCol<M>& z, double d, int hint)
+{
+    const double eps = 1e-8;
+    const int L = z.L;
+    LayerRes r;
+    if (hint >= 1 && hint <= L - 1) {
+        r.layer = hint;
+        r.top = z(hint - 1);
+        r.bot = z(hint);
+        // hint is the first match iff it matches and hint-1 does not (or hint == 1)
+        if (d >= r.bot - eps && d <= r.top + eps && (hint == 1 ? true : (d < r.top - eps))) return r;
+    }
+    r.top = 0.0; r.bot = 0.0;
+    if (d > z(0) + eps) { r.layer = 0; return r; }
+    int layer;
+    if (d < z(L - 1) - eps) {
+        layer = L - 1;
+    } else {
+        int lo = 1, hi = L - 1; // smallest k with d >= z[k]-eps; exists because d >= z[L-1]-eps
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (d >= z(mid) - eps) hi = mid;
+            else lo = mid + 1;
+        }
+        layer = lo;
+    }
+    r.layer = layer;
+    r.top = z(layer - 1);
+    r.bot = z(layer);
+    return r;
+}
+
+// TBBKernel::CalcVelocity + CalcAttribute on the packed (vx,vy,vz,w) records, TK:128-164
+template <int M>
+__device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, const int (&vo)[M], const double (&w)[M], int nv,
+                                            int layer, double& x, double& y, double& z, double& ww)
+{
+    x = 0.0; y = 0.0; z = 0.0; ww = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        if (i < nv) {
+            const double4 v = velw[vo[i] + layer];
+            x += w[i] * v.x;
+            y += w[i] * v.y;
+            z += w[i] * v.z;
+            ww += w[i] * v.w;
+        }
+    }
+}
+
+template <int M>
+__device__ __forceinline__ double gather_scalar(const double* __restrict__ a, const int (&vo)[M], const double (&w)[M], int nv, int layer)
+{
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+        if (i < nv) r += w[i] * a[vo[i] + layer];
+    return r;
+}
+
+struct EvalOut {
+    double hx, hy, hz; // horizontal velocity (XYZ)
+    double vv;         // vertical velocity
+    double a0, a1;     // pathline attributes
+};
+
+// calc_velocity_at (streamline), VK:740-872.  Returns ST_ALIVE or the reason of failure.
+template <int M>
+__device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, const SnapView& s, bool mono, int L,
+                                           const d3& p, double depth, int& hint, EvalOut& o)
+{
+    const int nv = rec->nv;
+    if (nv <= 0) return ST_BAD_SETUP;
+    double w[M];
+    bool wfinite = false;
+    if (!cell_weights<M>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    int vo[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+
+    LayerRes lr;
+    if (mono && wfinite) lr = layer_search_stream<M>(ZCol<M>{s.ztop, w, vo, nv, L}, depth, hint);
+    else lr = slow_layer_stream<M>(make_col_args<M>(s.ztop, w, vo, nv, L), depth);
+    const int layer = lr.layer;
+    const double ztop_up = lr.top, ztop_dn = lr.bot;
+    hint = layer;
+    // x = max(dn, min(depth, up)) with libstdc++ min/max semantics (VK:830-831)
+    const double mn = (ztop_up < depth) ? ztop_up : depth;
+    const double x = (ztop_dn < mn) ? mn : ztop_dn;
+    const double denom = ztop_up - ztop_dn;
+    if (fabs(denom) < 1e-12) return ST_BAD_COLUMN;
+    const double t = (x - ztop_dn) / denom;
+
+    double dx, dy, dz, dw, ux, uy, uz, uw;
+    gather_velw<M>(s.velw, vo, w, nv, layer, dx, dy, dz, dw);
+    gather_velw<M>(s.velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
+    if (len3(dx, dy, dz) < 1e-12 || len3(ux, uy, uz) < 1e-12) return ST_ZERO_VELOCITY; // VK:845-847
+    const double omt = 1.0 - t;
+    o.hx = t * ux + omt * dx; // VK:849
+    o.hy = t * uy + omt * dy;
+    o.hz = t * uz + omt * dz;
+    if (len3(o.hx, o.hy, o.hz) < 1e-12) return ST_ZERO_VELOCITY;
+    o.vv = t * uw + omt * dw; // VK:870 (levels `layer`, `layer-1` of vertVelocityTop)
+    o.a0 = 0.0; o.a1 = 0.0;
+    return ST_ALIVE;
+}
+
+// calc_velocity_at (pathline), VK:1124-1327: front and back interpolated separately (own layer
+// search each, shared weights), blended with alpha; no zero-velocity reject.
+template <int M>
+__device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, const SnapView& f, const SnapView& b,
+                                         bool mono_f, bool mono_b, int L, int attr_count, const d3& p, double depth,
+                                         double alpha, int& hint_f, int& hint_b, EvalOut& o)
+{
+    const int nv = rec->nv;
+    if (nv <= 0) return ST_BAD_SETUP;
+    double w[M];
+    bool wfinite = false;
+    if (!cell_weights<M>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    int vo[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+
+    LayerRes rf, rb;
+    if (mono_f && wfinite) rf = layer_search_path<M>(ZCol<M>{f.ztop, w, vo, nv, L}, depth, hint_f);
+    else rf = slow_layer_path<M>(make_col_args<M>(f.ztop, w, vo, nv, L), depth);
+    if (mono_b && wfinite) rb = layer_search_path<M>(ZCol<M>{b.ztop, w, vo, nv, L}, depth, hint_b);
+    else rb = slow_layer_path<M>(make_col_args<M>(b.ztop, w, vo, nv, L), depth);
+    const int lf = rf.layer, lb = rb.layer;
+    if (lf == 0 || lb == 0) return ST_ABOVE_SURFACE; // the reference reads ztop[-1] here (N2)
+    if (lf < 0 || lb < 0) return ST_BAD_COLUMN;
+    hint_f = lf;
+    hint_b = lb;
+    const double f_up = rf.top, f_dn = rf.bot, b_up = rb.top, b_dn = rb.bot;
+
+    double mn = (f_up < depth) ? f_up : depth;
+    const double x_front = (f_dn < mn) ? mn : f_dn;
+    const double denom_front = f_up - f_dn;
+    if (fabs(denom_front) < 1e-12) return ST_BAD_COLUMN;
+    const double t_front = (x_front - f_dn) / denom_front;
+    mn = (b_up < depth) ? b_up : depth;
+    const double x_back = (b_dn < mn) ? mn : b_dn;
+    const double denom_back = b_up - b_dn;
+    if (fabs(denom_back) < 1e-12) return ST_BAD_COLUMN;
+    const double t_back = (x_back - b_dn) / denom_back;
+
+    double dx, dy, dz, dw, ux, uy, uz, uw;
+    gather_velw<M>(f.velw, vo, w, nv, lf, dx, dy, dz, dw);
+    gather_velw<M>(f.velw, vo, w, nv, lf - 1, ux, uy, uz, uw);
+    const double omf = 1.0 - t_front;
+    const double ffx = t_front * ux + omf * dx, ffy = t_front * uy + omf * dy, ffz = t_front * uz + omf * dz;
+    const double w_front = t_front * uw + omf * dw;
+    gather_velw<M>(b.velw, vo, w, nv, lb, dx, dy, dz, dw);
+    gather_velw<M>(b.velw, vo, w, nv, lb - 1, ux, uy, uz, uw);
+    const double omb = 1.0 - t_back;
+    const double bbx = t_back * ux + omb * dx, bby = t_back * uy + omb * dy, bbz = t_back * uz + omb * dz;
+    const double w_back = t_back * uw + omb * dw;
+    const double oma = 1.0 - alpha;
+    o.hx = alpha * bbx + oma * ffx; // VK:1259
+    o.hy = alpha * bby + oma * ffy;
+    o.hz = alpha * bbz + oma * ffz;
+    o.vv = alpha * w_back + oma * w_front; // VK:1286
+    o.a0 = 0.0; o.a1 = 0.0;
+    if (attr_count >= 1) { // VK:1288-1306
+        const double adf = gather_scalar<M>(f.attr0, vo, w, nv, lf), auf = gather_scalar<M>(f.attr0, vo, w, nv, lf - 1);
+        const double a_front = t_front * auf + omf * adf;
+        const double adb = gather_scalar<M>(b.attr0, vo, w, nv, lb), aub = gather_scalar<M>(b.attr0, vo, w, nv, lb - 1);
+        const double a_back = t_back * aub + omb * adb;
+        o.a0 = alpha * a_back + oma * a_front;
+    }
+    if (attr_count >= 2) { // VK:1307-1323
+        const double adf = gather_scalar<M>(f.attr1, vo, w, nv, lf), auf = gather_scalar<M>(f.attr1, vo, w, nv, lf - 1);
+        const double a_front = t_front * auf + omf * adf;
+        const double adb = gather_scalar<M>(b.attr1, vo, w, nv, lb), aub = gather_scalar<M>(b.attr1, vo, w, nv, lb - 1);
+        const double a_back = t_back * aub + omb * adb;
+        o.a1 = alpha * a_back + oma * a_front;
+    }
+    return ST_ALIVE;
+}
+
+// ---- greedy nearest-centre walk (thread-serial form) -------------------------------------
+// On a Voronoi/Delaunay mesh every cell that is not the nearest generator to q has a
+// cellsOnCell neighbour strictly closer to q, so steepest descent on dist2 ends at the
+// exact nearest centre = what the reference's nanoflann 1-NN returns
+// (src/Core/MPASOGrid.cpp:287-313).
+template <int M>
+__device__ __forceinline__ int walk_nearest(const CellRec<M>* __restrict__ rec, const double4* __restrict__ c4, int start,
+                                            double qx, double qy, double qz)
+{
+    int cur = start;
+    double4 c = c4[cur];
+    double dcur = dist2(qx, qy, qz, c.x, c.y, c.z);
+    for (int it = 0; it < (1 << 22); ++it) {
+        const CellRec<M>* r = rec + cur;
+        const int nv = r->nv;
+        int best = cur;
+        double dbest = dcur;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            if (k < nv) {
+                const int nb = r->nbr[k];
+                if (nb >= 0) {
+                    const double4 cc = c4[nb];
+                    const double d = dist2(qx, qy, qz, cc.x, cc.y, cc.z);
+                    if (d < dbest) {
+                        dbest = d;
+                        best = nb;
+                    }
+                }
+            }
+        }
+        if (best == cur) break;
+        cur = best;
+        dcur = dbest;
+    }
+    return cur;
+}
+
+// direction -> cube-map bucket (start guess of the walk; float precision is enough)
+__device__ __forceinline__ int cube_bucket(double x, double y, double z, int F)
+{
+    const double axx = fabs(x), ayy = fabs(y), azz = fabs(z);
+    int face;
+    double ma, u, v;
+    if (axx >= ayy && axx >= azz) { face = x >= 0 ? 0 : 1; ma = axx; u = y; v = z; }
+    else if (ayy >= azz)          { face = y >= 0 ? 2 : 3; ma = ayy; u = x; v = z; }
+    else                          { face = z >= 0 ? 4 : 5; ma = azz; u = x; v = y; }
+    const float inv = 1.0f / (float)ma;
+    int i = (int)(((float)u * inv * 0.5f + 0.5f) * (float)F);
+    int j = (int)(((float)v * inv * 0.5f + 0.5f) * (float)F);
+    i = min(max(i, 0), F - 1);
+    j = min(max(j, 0), F - 1);
+    return (face * F + i) * F + j;
+}
+
+// centre direction of bucket (face, i, j)
+__device__ __forceinline__ void cube_center(int face, int i, int j, int F, double& x, double& y, double& z)
+{
+    const double u = ((double)i + 0.5) / (double)F * 2.0 - 1.0;
+    const double v = ((double)j + 0.5) / (double)F * 2.0 - 1.0;
+    const double s = (face & 1) ? -1.0 : 1.0;
+    if (face < 2)      { x = s; y = u; z = v; }
+    else if (face < 4) { x = u; y = s; z = v; }
+    else               { x = u; y = v; z = s; }
+}
+
+} // namespace mops

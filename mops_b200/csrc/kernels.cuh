@@ -1,0 +1,662 @@
+// kernels.cuh -- every __global__ kernel of the engine (sm_100a).  Host-side launch logic is
+// in engine.cu.  VK = src/CPU/TBB/Kernel/MPASOVisualizerKernels.cpp, TK = .../TBBKernel.h,
+// ST = src/CPU/TBB/MPASOSolutionTBB.cpp of the reference.
+#pragma once
+#include "engine.cuh"
+
+namespace mops {
+
+// =========================================================================================
+// mesh set-up kernels (run once per mesh)
+// =========================================================================================
+
+// point-independent parts of IsInMesh (TK:40-47) and of Wachspress (Interpolation.hpp:154)
+template <int M>
+__global__ void k_build_records(CellRec<M>* __restrict__ rec, int nC)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    CellRec<M>* r = rec + c;
+    const int nv = r->nv;
+    for (int k = 0; k < M; ++k) {
+        if (k < nv) {
+            const int kn = (k + 1) % nv;
+            const int kp = (k - 1 + nv) % nv;
+            const double ax = r->vx[k], ay = r->vy[k], az = r->vz[k];
+            const double bx = r->vx[kn], by = r->vy[kn], bz = r->vz[kn];
+            r->nx[k] = ay * bz - az * by; // cy::Vec3::Cross
+            r->ny[k] = az * bx - ax * bz;
+            r->nz[k] = ax * by - ay * bx;
+            r->B[k] = tri_area(r->vx[kp], r->vy[kp], r->vz[kp], ax, ay, az, bx, by, bz);
+        } else {
+            r->nx[k] = 0.0; r->ny[k] = 0.0; r->nz[k] = 0.0; r->B[k] = 0.0;
+        }
+    }
+}
+
+// coefficients of GeoConverter::convertENUVelocityToXYZ (GeoConverter.hpp:225-250) at a cell
+// centre, stored in the CALLER's cell order: (slon, clon, slat, clat); slon = NaN flags the
+// x == y == 0 singularity branch.
+__global__ void k_cell_trig(const double* __restrict__ cell_xyz_ext, double4* __restrict__ trig, int nC)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const double x = cell_xyz_ext[3 * (size_t)c], y = cell_xyz_ext[3 * (size_t)c + 1], z = cell_xyz_ext[3 * (size_t)c + 2];
+    double4 t;
+    if (x == 0.0 && y == 0.0) {
+        t.x = nan(""); t.y = 0.0; t.z = 0.0; t.w = 0.0;
+    } else {
+        const double Rxy = sqrt(x * x + y * y);
+        const double Rxyz = sqrt(x * x + y * y + z * z);
+        t.x = y / Rxy;    // slon
+        t.y = x / Rxy;    // clon
+        t.z = z / Rxyz;   // slat
+        t.w = Rxy / Rxyz; // clat
+    }
+    trig[c] = t;
+}
+
+// Interpolator::calcTriangleBarycentric of each Voronoi vertex in the triangle of its three
+// cell centres (Interpolation.hpp:79-93); mesh-constant, so computed once instead of once per
+// (vertex, level) as ST:42-52 does.
+__global__ void k_vert_bary(VertRec* __restrict__ vert, const int* __restrict__ vext, const double* __restrict__ vertex_xyz_ext,
+                            const double* __restrict__ cell_xyz_ext, const int* __restrict__ vcell_ext, int nV)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    VertRec r = vert[v];
+    r.u = 0.0; r.v = 0.0; r.w = 0.0;
+    if (!r.boundary) {
+        const size_t ve = (size_t)vext[v];
+        const double px = vertex_xyz_ext[3 * ve], py = vertex_xyz_ext[3 * ve + 1], pz = vertex_xyz_ext[3 * ve + 2];
+        const size_t e0 = (size_t)vcell_ext[3 * (size_t)v], e1 = (size_t)vcell_ext[3 * (size_t)v + 1], e2 = (size_t)vcell_ext[3 * (size_t)v + 2];
+        const double t0x = cell_xyz_ext[3 * e0], t0y = cell_xyz_ext[3 * e0 + 1], t0z = cell_xyz_ext[3 * e0 + 2];
+        const double v0x = cell_xyz_ext[3 * e1] - t0x, v0y = cell_xyz_ext[3 * e1 + 1] - t0y, v0z = cell_xyz_ext[3 * e1 + 2] - t0z;
+        const double v1x = cell_xyz_ext[3 * e2] - t0x, v1y = cell_xyz_ext[3 * e2 + 1] - t0y, v1z = cell_xyz_ext[3 * e2 + 2] - t0z;
+        const double v2x = px - t0x, v2y = py - t0y, v2z = pz - t0z;
+        const double d00 = v0x * v0x + v0y * v0y + v0z * v0z;
+        const double d01 = v0x * v1x + v0y * v1y + v0z * v1z;
+        const double d11 = v1x * v1x + v1y * v1y + v1z * v1z;
+        const double d20 = v2x * v0x + v2y * v0y + v2z * v0z;
+        const double d21 = v2x * v1x + v2y * v1y + v2z * v1z;
+        const double denom = d00 * d11 - d01 * d01;
+        r.v = (d11 * d20 - d01 * d21) / denom;
+        r.w = (d00 * d21 - d01 * d20) / denom;
+        r.u = 1.0 - r.v - r.w;
+    }
+    vert[v] = r;
+}
+
+// cube-map start table of the locate walk, built coarse-to-fine: bucket (face,i,j) at
+// resolution F starts its walk from the parent bucket's answer at resolution F/2.
+template <int M>
+__global__ void k_cube_level(const CellRec<M>* __restrict__ rec, const double4* __restrict__ c4, const int* __restrict__ parent,
+                             int* __restrict__ table, int F, double radius)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 6 * F * F) return;
+    const int face = id / (F * F);
+    const int i = (id / F) % F;
+    const int j = id % F;
+    double x, y, z;
+    cube_center(face, i, j, F, x, y, z);
+    const double s = radius / sqrt(x * x + y * y + z * z);
+    const int start = parent ? parent[(face * (F / 2) + i / 2) * (F / 2) + j / 2] : 0;
+    table[id] = walk_nearest<M>(rec, c4, start, x * s, y * s, z * s);
+}
+
+// =========================================================================================
+// point location: 8 lanes cooperate on one query (one lane per cellsOnCell neighbour)
+// replaces MPASOField::calcInWhichCells (src/Core/MPASOField.cpp:23-34)
+// =========================================================================================
+template <int M>
+__global__ void __launch_bounds__(256) k_locate(const CellRec<M>* __restrict__ rec, const double4* __restrict__ c4,
+                                                const int* __restrict__ cube, int F, int nC,
+                                                long long n, const double* __restrict__ xyz,
+                                                int* __restrict__ cell_int, int* __restrict__ cell_ext,
+                                                const int* __restrict__ c_int2ext)
+{
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    if (gid >= n) return; // whole 8-lane group exits together
+    const double qx = xyz[3 * gid], qy = xyz[3 * gid + 1], qz = xyz[3 * gid + 2];
+    int result = -1;
+    if (finite3(qx, qy, qz)) {
+        int cur = cube[cube_bucket(qx, qy, qz, F)];
+        double4 c = c4[cur];
+        double dcur = dist2(qx, qy, qz, c.x, c.y, c.z);
+        for (int it = 0; it < (1 << 22); ++it) {
+            const CellRec<M>* r = rec + cur;
+            const int nv = r->nv;
+            double dbest = dcur;
+            int best = cur;
+            for (int base = 0; base < nv; base += 8) { // one pass for nv <= 8
+                const int k = base + sub;
+                if (k < nv) {
+                    const int nb = r->nbr[k];
+                    if (nb >= 0) {
+                        const double4 cc = c4[nb];
+                        const double d = dist2(qx, qy, qz, cc.x, cc.y, cc.z);
+                        if (d < dbest) { dbest = d; best = nb; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) { // argmin over the 8 lanes (ties -> lower cell id)
+                const double od = __shfl_xor_sync(gmask, dbest, off, 8);
+                const int ob = __shfl_xor_sync(gmask, best, off, 8);
+                if (od < dbest || (od == dbest && ob < best)) { dbest = od; best = ob; }
+            }
+            if (!(dbest < dcur)) break;
+            cur = best;
+            dcur = dbest;
+        }
+        result = cur;
+    }
+    if (sub == 0) {
+        if (cell_int) cell_int[gid] = result;
+        if (cell_ext) cell_ext[gid] = result >= 0 ? c_int2ext[result] : -1;
+    }
+}
+
+// caller cell ids -> internal ids (and back)
+__global__ void k_map_ids(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ map, int nmap, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = in[i];
+    out[i] = (c >= 0 && c < nmap) ? map[c] : -1;
+}
+
+__global__ void k_iota(int* __restrict__ a, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int)i;
+}
+
+// =========================================================================================
+// snapshot preprocessing (a17) -- replaces MOPSApp::addSol's chain, src/Core/MOPSApp.cpp:100-130
+// =========================================================================================
+
+// MPASOSolution::calcCellCenterZtop, bottomDepth branch (src/Core/MPASOSolution.cpp:565-577):
+// sequential bottom-up sum, so one thread per cell.
+__global__ void k_cell_ztop(const double* __restrict__ thick, const double* __restrict__ bottom, double* __restrict__ ztop_c, int nC, int L)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    double z = -bottom[c];
+    const size_t row = (size_t)c * L;
+    for (int k = L - 1; k >= 0; --k) {
+        z += thick[row + k];
+        ztop_c[row + k] = z * 1.0;
+    }
+}
+
+// CalcCellVertexZtop (ST:9-55) + CalcCellCenterVelocityByZM (ST:108-129) + CalcCellVertexVelocity
+// (ST:270-318) + CalcCellVertexVertVelocity (ST:320-366) fused: one thread per (vertex, level),
+// level fastest so reads of the three cell rows and the writes are coalesced along k.
+__global__ void k_vertex_fields(const VertRec* __restrict__ vert, const int* __restrict__ vcell_ext, const double4* __restrict__ trig,
+                                const double* __restrict__ ztop_c, const double* __restrict__ zonal, const double* __restrict__ merid,
+                                const double* __restrict__ wtop, double* __restrict__ ztop_v, double4* __restrict__ velw_v,
+                                int nV, int L)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nV * L) return;
+    const int v = (int)(idx / L);
+    const int k = (int)(idx % L);
+    const VertRec r = vert[v];
+    double zt = 0.0;
+    double4 o = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (!r.boundary) {
+        double zc[3], wc[3], vx[3], vy[3], vz[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const size_t e = (size_t)vcell_ext[3 * (size_t)v + t];
+            zc[t] = ztop_c[e * L + k];
+            wc[t] = wtop ? wtop[e * (L + 1) + k] : 0.0;
+            const double Uzon = zonal[e * L + k], Umer = merid[e * L + k], Uup = 0.0;
+            const double4 tr = trig[e];
+            if (isnan(tr.x)) {
+                vx[t] = 0.0; vy[t] = 0.0; vz[t] = Uup;
+            } else {
+                const double slon = tr.x, clon = tr.y, slat = tr.z, clat = tr.w;
+                vx[t] = -slon * Uzon - slat * clon * Umer + clon * clat * Uup;
+                vy[t] = clon * Uzon - slat * slon * Umer + slon * clat * Uup;
+                vz[t] = clat * Umer + slat * Uup;
+            }
+        }
+        zt = r.u * zc[0] + r.v * zc[1] + r.w * zc[2];
+        o.x = vx[0] * r.u + vx[1] * r.v + vx[2] * r.w;
+        o.y = vy[0] * r.u + vy[1] * r.v + vy[2] * r.w;
+        o.z = vz[0] * r.u + vz[1] * r.v + vz[2] * r.w;
+        o.w = r.u * wc[0] + r.v * wc[1] + r.w * wc[2];
+    }
+    ztop_v[idx] = zt;
+    velw_v[idx] = o;
+}
+
+// CalcCellCenterToVertex (ST:57-106): scalar attribute, clamped >= 0
+__global__ void k_vertex_scalar(const VertRec* __restrict__ vert, const int* __restrict__ vcell_ext, const double* __restrict__ cell_val,
+                                double* __restrict__ vert_val, int nV, int L)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nV * L) return;
+    const int v = (int)(idx / L);
+    const int k = (int)(idx % L);
+    const VertRec r = vert[v];
+    double out = 0.0;
+    if (!r.boundary) {
+        const double a = cell_val[(size_t)vcell_ext[3 * (size_t)v] * L + k];
+        const double b = cell_val[(size_t)vcell_ext[3 * (size_t)v + 1] * L + k];
+        const double c = cell_val[(size_t)vcell_ext[3 * (size_t)v + 2] * L + k];
+        out = r.u * a + r.v * b + r.w * c;
+        if (out < 0.0) out = 0.0;
+    }
+    vert_val[idx] = out;
+}
+
+// per-vertex: is the zTop column finite and non-increasing?  (one warp per vertex)
+__global__ void k_vertex_mono(const double* __restrict__ ztop_v, unsigned char* __restrict__ vmono, int nV, int L)
+{
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= nV) return;
+    const double* col = ztop_v + (size_t)gw * L;
+    bool ok = true;
+    for (int k = lane; k < L; k += 32) {
+        const double a = col[k];
+        if (!isfinite(a)) ok = false;
+        if (k > 0 && a > col[k - 1]) ok = false;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) vmono[gw] = ok ? 1 : 0;
+}
+
+template <int M>
+__global__ void k_cell_mono(const CellRec<M>* __restrict__ rec, const unsigned char* __restrict__ vmono, unsigned char* __restrict__ cmono,
+                            int nC, int* __restrict__ n_nonmono)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const CellRec<M>* r = rec + c;
+    bool ok = true;
+    for (int k = 0; k < r->nv; ++k) ok = ok && (vmono[r->vid[k]] != 0);
+    cmono[c] = ok ? 1 : 0;
+    if (!ok) atomicAdd(n_nonmono, 1);
+}
+
+// vertex-major arrays back in the caller's vertex order (parity tests)
+__global__ void k_export_prepared(const int* __restrict__ v_ext2int, const double* __restrict__ ztop_v, const double4* __restrict__ velw_v,
+                                  const double* __restrict__ a0, const double* __restrict__ a1,
+                                  double* __restrict__ o_ztop, double* __restrict__ o_vel, double* __restrict__ o_w,
+                                  double* __restrict__ o_a0, double* __restrict__ o_a1, int nV, int L)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nV * L) return;
+    const int ve = (int)(idx / L);
+    const int k = (int)(idx % L);
+    const size_t src = (size_t)v_ext2int[ve] * L + k;
+    if (o_ztop) o_ztop[idx] = ztop_v[src];
+    const double4 q = velw_v[src];
+    if (o_vel) { o_vel[3 * idx] = q.x; o_vel[3 * idx + 1] = q.y; o_vel[3 * idx + 2] = q.z; }
+    if (o_w) {
+        o_w[(size_t)ve * (L + 1) + k] = q.w;
+        if (k == L - 1) o_w[(size_t)ve * (L + 1) + L] = 0.0;
+    }
+    if (o_a0 && a0) o_a0[idx] = a0[src];
+    if (o_a1 && a1) o_a1[idx] = a1[src];
+}
+
+// =========================================================================================
+// streamline / pathline: one thread integrates one particle over all steps of the call
+// (StreamLine VK:874-1003, PathLine VK:1329-1483)
+// =========================================================================================
+struct AdvectParams {
+    const void* rec;
+    const double4* c4;
+    const int* c_int2ext;
+    int nC, L;
+    SnapView f, b;
+    int attr_count;   // pathline attributes in use (0..2)
+    int use_euler;
+    int delta_t;      // signed seconds
+    int times;        // steps
+    int each;         // recorded slots per particle
+    int record_t;     // seconds (streamline: run_time % record_t == 0)
+    int record_interval; // pathline: (step+1) % (record_t/delta_t) == 0
+    double duration;  // simulationDuration (pathline dalpha)
+    long long n;
+    const int* order; // processing order (particle indices sorted by start cell) or null
+    double* pos;      // [n][3] in/out
+    float* depth;     // [n]    in/out
+    const int* cell0; // [n] internal start cells
+    double* out_pos;  // [n][each][3] (zero-initialised by the host)
+    double* out_vel;
+    double* out_attr; // or null
+    int* cell_log;    // [n][times] caller cell ids, or null
+    int* status;      // or null
+    int* steps;       // or null
+    int* fcell;       // or null (caller cell ids)
+    unsigned long long* counters; // [0] particle-steps started, [1] alive at end
+};
+
+__device__ __forceinline__ void st3(double* p, long long i, double x, double y, double z)
+{
+    p[3 * i] = x; p[3 * i + 1] = y; p[3 * i + 2] = z;
+}
+
+__device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : ((1.0 < v) ? 1.0 : v); }
+
+template <int M, bool PATH>
+__global__ void __launch_bounds__(128) k_advect(const AdvectParams P)
+{
+    const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long my_steps = 0, my_alive = 0;
+    if (tix < P.n) {
+        const long long pid = P.order ? (long long)P.order[tix] : tix;
+        const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
+        d3 pos = mk3(P.pos[3 * pid], P.pos[3 * pid + 1], P.pos[3 * pid + 2]);
+        float depth_f = P.depth[pid];
+        int cell = P.cell0[pid];
+        const long long base = pid * (long long)P.each;
+        const double dt = (double)P.delta_t;
+        const double dalpha = PATH ? dt / P.duration : 0.0; // VK:1401
+        int status = ST_ALIVE;
+        int started = 0;
+        int run_time = 0;
+        int upd = 0;
+        int hint_f = -1, hint_b = -1;
+        bool first_vel = true;
+
+        if (cell < 0 || cell >= P.nC) {
+            status = ST_BAD_CELL; // VK:895-897: nothing is written, not even the seed
+        } else {
+            st3(P.out_pos, base, pos.x, pos.y, pos.z); // VK:901
+            for (int step = 0; step < P.times; ++step) {
+                run_time += abs(P.delta_t);
+                if (step > 0) {
+                    // relocation: argmin over {cellsOnCell[c][0..nv-1], c} of |centre - x|, strict <,
+                    // that order, one ring (VK:903-921; GetCellNeighborsIdx TK:74-101)
+                    const CellRec<M>* r = recs + cell;
+                    const int nv = r->nv;
+                    double min_len = 1.7976931348623157e308;
+                    int best = cell;
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        if (k < nv) {
+                            const int cid = r->nbr[k];
+                            if (cid >= 0) {
+                                const double4 cc = P.c4[cid];
+                                const double len = len3(cc.x - pos.x, cc.y - pos.y, cc.z - pos.z);
+                                if (len < min_len) { min_len = len; best = cid; }
+                            }
+                        }
+                    }
+                    {
+                        const double4 cc = P.c4[cell];
+                        const double len = len3(cc.x - pos.x, cc.y - pos.y, cc.z - pos.z);
+                        if (len < min_len) { min_len = len; best = cell; }
+                    }
+                    if (best != cell) { cell = best; }
+                }
+                ++started;
+                if (P.cell_log) P.cell_log[pid * (long long)P.times + step] = P.c_int2ext[cell];
+
+                const CellRec<M>* __restrict__ rec = recs + cell;
+                const bool mono_f = P.f.mono[cell] != 0;
+                const bool mono_b = PATH ? (P.b.mono[cell] != 0) : false;
+                const double cur_depth = -1.0 * (double)depth_f;
+                const double alpha = PATH ? (double)step / (double)P.times : 0.0; // VK:1345
+                const double r = len3(pos);
+                d3 hvel = mk3(0.0, 0.0, 0.0);
+                double vvel = 0.0, at0 = 0.0, at1 = 0.0;
+                d3 new_pos;
+                EvalOut o;
+
+                if (P.use_euler) {
+                    const int st = PATH ? eval_path<M>(rec, P.f, P.b, mono_f, mono_b, P.L, P.attr_count, pos, cur_depth, alpha, hint_f, hint_b, o)
+                                        : eval_stream<M>(rec, P.f, mono_f, P.L, pos, cur_depth, hint_f, o);
+                    if (st != ST_ALIVE) { status = st; break; }
+                    hvel = mk3(o.hx, o.hy, o.hz);
+                    vvel = o.vv; at0 = o.a0; at1 = o.a1;
+                    new_pos = rotate_euler(pos, hvel, P.delta_t, r); // VK:968-972
+                } else {
+                    // RK4: all four stages against the start-of-step cell (VK:939-957, R1)
+                    d3 hprev = mk3(0.0, 0.0, 0.0);
+                    int st = ST_ALIVE;
+#pragma unroll 1
+                    for (int s = 0; s < 4; ++s) {
+                        d3 p = pos;
+                        double a_s = alpha;
+                        if (s > 0) {
+                            p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5);
+                            if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
+                        }
+                        st = PATH ? eval_path<M>(rec, P.f, P.b, mono_f, mono_b, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                                  : eval_stream<M>(rec, P.f, mono_f, P.L, p, cur_depth, hint_f, o);
+                        if (st != ST_ALIVE) break;
+                        if (s == 0) {
+                            hvel = mk3(o.hx, o.hy, o.hz);
+                            vvel = o.vv; at0 = o.a0; at1 = o.a1;
+                        } else {
+                            const double c = (s == 3) ? 1.0 : 2.0; // s1 + 2 s2 + 2 s3 + s4, left to right (VK:959-960)
+                            hvel.x = hvel.x + c * o.hx;
+                            hvel.y = hvel.y + c * o.hy;
+                            hvel.z = hvel.z + c * o.hz;
+                            vvel = vvel + c * o.vv;
+                            at0 = at0 + c * o.a0;
+                            at1 = at1 + c * o.a1;
+                        }
+                        hprev = mk3(o.hx, o.hy, o.hz);
+                    }
+                    if (st != ST_ALIVE) { status = st; break; }
+                    hvel.x = hvel.x / 6.0; hvel.y = hvel.y / 6.0; hvel.z = hvel.z / 6.0;
+                    vvel = vvel / 6.0;
+                    at0 = at0 / 6.0; at1 = at1 / 6.0;
+                    const double tx = pos.x + hvel.x * dt, ty = pos.y + hvel.y * dt, tz = pos.z + hvel.z * dt; // VK:962-964
+                    const double tl = len3(tx, ty, tz);
+                    if (tl > 1e-12) new_pos = mk3((tx / tl) * r, (ty / tl) * r, (tz / tl) * r);
+                    else new_pos = pos;
+                }
+
+                if (first_vel) { // VK:988-991 / VK:1449-1456
+                    first_vel = false;
+                    st3(P.out_vel, base, hvel.x, hvel.y, hvel.z);
+                    if (PATH && P.attr_count > 0 && P.out_attr) st3(P.out_attr, base, at0, at1, 0.0);
+                }
+
+                // depth / radius update with the float round trip (VK:977-986, R3, R4)
+                const double old_depth = (double)depth_f;
+                double new_depth = old_depth - vvel * (double)P.delta_t;
+                new_depth = (0.0 < new_depth) ? new_depth : 0.0;
+                const double r_sum = r + vvel * (double)P.delta_t;
+                const double r_new = (1.0 < r_sum) ? r_sum : 1.0;
+                depth_f = (float)new_depth;
+                const double nlen = len3(new_pos);
+                if (nlen > 1e-12) new_pos = mk3((new_pos.x / nlen) * r_new, (new_pos.y / nlen) * r_new, (new_pos.z / nlen) * r_new);
+                pos = new_pos;
+
+                bool rec_now;
+                if (PATH) rec_now = (P.record_interval > 0) && (((step + 1) % P.record_interval) == 0); // VK:1470-1471
+                else rec_now = (run_time % P.record_t) == 0;                                              // VK:994
+                if (rec_now) {
+                    if (upd < P.each) {
+                        st3(P.out_pos, base + upd, pos.x, pos.y, pos.z);
+                        st3(P.out_vel, base + upd, hvel.x, hvel.y, hvel.z);
+                        if (PATH && P.attr_count > 0 && P.out_attr) st3(P.out_attr, base + upd, at0, at1, 0.0);
+                    }
+                    ++upd;
+                }
+            }
+        }
+        P.pos[3 * pid] = pos.x; P.pos[3 * pid + 1] = pos.y; P.pos[3 * pid + 2] = pos.z;
+        P.depth[pid] = depth_f;
+        if (P.status) P.status[pid] = status;
+        if (P.steps) P.steps[pid] = started;
+        if (P.fcell) P.fcell[pid] = (cell >= 0 && cell < P.nC) ? P.c_int2ext[cell] : -1;
+        my_steps = (unsigned long long)started;
+        my_alive = (status == ST_ALIVE) ? 1ull : 0ull;
+    }
+    // one atomic pair per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
+        my_alive += __shfl_xor_sync(0xffffffffu, my_alive, off);
+    }
+    if ((threadIdx.x & 31) == 0 && P.counters) {
+        atomicAdd(P.counters + 0, my_steps);
+        atomicAdd(P.counters + 1, my_alive);
+    }
+}
+
+// =========================================================================================
+// remap: one thread per pixel -- pixel -> lat/lon -> XYZ -> locate -> IsInMesh -> Wachspress
+// -> depth test -> 2-layer velocity blend -> ENU (VisualizeFixedDepth, VK:238-471; replaces the
+// serial host KD loop TBBKernel::SearchKDTree as well)
+// =========================================================================================
+struct RemapParams {
+    const void* rec;
+    const double4* c4;
+    const int* cube;
+    const int* c_int2ext;
+    int F, nC, L;
+    SnapView s;
+    int attr_count;  // number of attribute arrays available (0..2)
+    int attr_image;  // 1 = write img1 (reference: mDoubleAttributes.size() > 1)
+    int width, height;
+    double minLat, maxLat, minLon, maxLon;
+    double DEPTH;    // -FixedDepth
+    double* img0;
+    double* img1;
+    int* pixel_cell; // caller ids or null
+    unsigned long long* nan_count;
+};
+
+__device__ __forceinline__ void put_pixel(double* img, long long gid, double a, double b, double c)
+{
+    double4* p = reinterpret_cast<double4*>(img) + gid; // (i*w + j)*4 doubles; cudaMalloc'd => 32 B aligned
+    *p = make_double4(a, b, c, 1.0);
+}
+
+template <int M>
+__global__ void __launch_bounds__(128) k_remap(const RemapParams P)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.width * P.height) return;
+    const int ih = (int)(gid / P.width);
+    const int jw = (int)(gid % P.width);
+    // GeoConverter::convertPixelToLatLonToRadians + convertRadianLatLonToXYZ (GeoConverter.hpp:9-33,107-125)
+    double lat = P.maxLat - ((double)ih / (double)P.height * (P.maxLat - P.minLat));
+    double lon = ((double)jw / (double)P.width * (P.maxLon - P.minLon)) + P.minLon;
+    lat = lat * (3.14159265358979323846 / 180.0);
+    lon = lon * (3.14159265358979323846 / 180.0);
+    const double rr = 6371010.0;
+    double sintheta, costheta, sinphi, cosphi;
+    sincos(lat, &sintheta, &costheta);
+    sincos(lon, &sinphi, &cosphi);
+    d3 pos;
+    pos.x = rr * costheta * cosphi;
+    pos.y = rr * costheta * sinphi;
+    pos.z = rr * sintheta;
+
+    const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
+    const double nanv = nan("");
+    int cell = -1;
+    if (finite3(pos.x, pos.y, pos.z)) cell = walk_nearest<M>(recs, P.c4, P.cube[cube_bucket(pos.x, pos.y, pos.z, P.F)], pos.x, pos.y, pos.z);
+    if (P.pixel_cell) P.pixel_cell[gid] = cell >= 0 ? P.c_int2ext[cell] : -1;
+
+    bool ok = (cell >= 0 && cell < P.nC);
+    double u_east = 0.0, v_north = 0.0, spd = 0.0, a0 = 0.0, a1 = 0.0;
+    if (ok) {
+        const CellRec<M>* __restrict__ rec = recs + cell;
+        const int nv = rec->nv;
+        const int L = P.L;
+        double w[M];
+        bool wfinite = false;
+        ok = (nv > 0) && cell_weights<M>(rec, nv, pos.x, pos.y, pos.z, w, wfinite);
+        if (ok) {
+            int vo[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+            const double DEPTH = P.DEPTH;
+            int local_layer = -1;
+            double topI = 0.0, botI = 0.0;
+            if ((P.s.mono[cell] != 0) && wfinite) {
+                // non-increasing column: only z[0], z[1], z[L-1] are ever needed
+                const ZCol<M> z{P.s.ztop, w, vo, nv, L};
+                const double zs = z(0), zb = z(L - 1);
+                double z_surf = zs, z_bot = zb;
+                if (z_surf < z_bot) { const double t = z_surf; z_surf = z_bot; z_bot = t; }
+                const double ad = 1e-8 * fabs(z_surf - z_bot);
+                const double epsd = (1e-6 < ad) ? ad : 1e-6;
+                if (!(DEPTH <= z_surf + epsd && DEPTH >= z_bot - epsd)) ok = false;
+                if (ok) {
+                    if (DEPTH <= zs) {
+                        local_layer = 0; // VK:392-394
+                        topI = zs; botI = zs;
+                    } else {
+                        const double z1 = z(1);
+                        // DEPTH > z[0] >= z[k]: layer 1 matches iff DEPTH <= z[0]+1e-8; if it does not,
+                        // no later layer can (their tops are <= z[0]) and the pixel is NaN (VK:378-401)
+                        if (DEPTH <= zs + 1e-8 && DEPTH >= z1 - 1e-8) { local_layer = 1; topI = zs; botI = z1; }
+                    }
+                }
+            } else {
+                const LayerRes lr = slow_layer_remap<M>(make_col_args<M>(P.s.ztop, w, vo, nv, L), DEPTH);
+                local_layer = lr.layer; topI = lr.top; botI = lr.bot;
+                if (lr.layer == -2) { ok = false; local_layer = -1; }
+            }
+            if (local_layer < 0) ok = false;
+            if (ok) {
+                if (topI < botI) { const double t = topI; topI = botI; botI = t; }
+                const double denom = topI - botI;
+                const double tparam = (denom > 1e-12) ? (DEPTH - botI) / denom : 0.5; // VK:411-412
+                int j = local_layer - 1;
+                if (j < 0) j = 0;
+                if (j > L - 1) j = L - 1;
+                const int j_bot = (j + 1 < L - 1) ? j + 1 : L - 1;
+                const int j_top = j;
+                double tx, ty, tz, tw, bx, by, bz, bw;
+                gather_velw<M>(P.s.velw, vo, w, nv, j_top, tx, ty, tz, tw);
+                gather_velw<M>(P.s.velw, vo, w, nv, j_bot, bx, by, bz, bw);
+                const double mtop = len3(tx, ty, tz), mbot = len3(bx, by, bz);
+                double fx, fy, fz;
+                if (mtop < 1e-12 && mbot < 1e-12) { fx = 0.0; fy = 0.0; fz = 0.0; }
+                else if (mtop < 1e-12) { fx = bx; fy = by; fz = bz; }
+                else if (mbot < 1e-12) { fx = tx; fy = ty; fz = tz; }
+                else {
+                    const double omt = 1.0 - tparam;
+                    fx = omt * bx + tparam * tx; // VK:435
+                    fy = omt * by + tparam * ty;
+                    fz = omt * bz + tparam * tz;
+                }
+                // GeoConverter::convertXYZVelocityToENU (GeoConverter.hpp:200-223)
+                if (pos.x == 0.0 && pos.y == 0.0) {
+                    u_east = 0.0; v_north = 0.0;
+                } else {
+                    const double Rxy = sqrt(pos.x * pos.x + pos.y * pos.y);
+                    const double Rxyz = sqrt(pos.x * pos.x + pos.y * pos.y + pos.z * pos.z);
+                    const double slon = pos.y / Rxy, clon = pos.x / Rxy, slat = pos.z / Rxyz, clat = Rxy / Rxyz;
+                    u_east = -slon * fx + clon * fy;
+                    v_north = -slat * (clon * fx + slon * fy) + clat * fz;
+                }
+                spd = sqrt(u_east * u_east + v_north * v_north);
+                if (P.attr_image) { // VK:443-464: attributes from layer max(local_layer-1, 0)
+                    if (P.attr_count >= 1) a0 = gather_scalar<M>(P.s.attr0, vo, w, nv, j);
+                    if (P.attr_count >= 2) a1 = gather_scalar<M>(P.s.attr1, vo, w, nv, j);
+                }
+            }
+        }
+    }
+    if (ok) {
+        put_pixel(P.img0, gid, u_east, v_north, spd);
+        if (P.attr_image && P.img1) put_pixel(P.img1, gid, a0, a1, 0.0);
+    } else {
+        put_pixel(P.img0, gid, nanv, nanv, nanv);
+        if (P.attr_image && P.img1) put_pixel(P.img1, gid, nanv, nanv, nanv);
+        if (P.nan_count) atomicAdd(P.nan_count, 1ull);
+    }
+}
+
+} // namespace mops

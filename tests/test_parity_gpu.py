@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmops_b200.so via ctypes),
+against the oracle (oracle/mops_oracle.c, itself pinned bit-for-bit to the compiled reference)
+on the same seeded inputs.
+
+Bars (BASELINE.json north_star): cell-ID sequences and remap pixel cell IDs bit-exact except
+for points within 1e-12 rad of a cell edge (counted); positions within 1 m; velocities within
+1e-9 relative.  In practice everything except sin/cos is bit-identical, so the tests also
+assert much tighter bounds and report the exact-match fraction.
+"""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+DT, DAY = 120, 86400
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from mops_b200 import capi
+    e = capi.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def P():
+    from oracle import port_oracle
+    return port_oracle
+
+
+def _setup(eng, level, L, variant):
+    m = cases.mesh(level)
+    s0, s1 = cases.snapshots(level, L, variant)
+    eng.set_mesh(m)
+    eng.set_snapshot(0, s0)
+    eng.set_snapshot(1, s1)
+    return m, s0, s1
+
+
+@pytest.mark.parametrize("variant", ["plain", "rich", "nonmono"])
+def test_prepare_bit_exact(eng, P, variant):
+    m, s0, s1 = _setup(eng, 4, 12, variant)
+    for slot, s in ((0, s0), (1, s1)):
+        ref = P.prepare(m, s)
+        na = min(2, len(s.attrs))
+        got = eng.get_prepared(slot, attrs=na)
+        assert np.array_equal(got["ztop_vertex"], ref.ztop_v)
+        assert np.array_equal(got["vel_vertex"], ref.vel_v)
+        assert np.array_equal(got["vertvel_vertex"][:, :-1], ref.w_v[:, :-1])
+        names = sorted(s.attrs)
+        if na >= 1:
+            assert np.array_equal(got["attr0"], ref.attrs_v[names[0]])
+        if na >= 2:
+            assert np.array_equal(got["attr1"], ref.attrs_v[names[1]])
+    info = eng.info()
+    if variant == "nonmono":
+        assert info.nonmonotone_cells[0] > 0
+    else:
+        assert info.nonmonotone_cells[0] == 0
+
+
+@pytest.mark.parametrize("level", [3, 5])
+def test_locate_exact(eng, P, level):
+    m = cases.mesh(level)
+    eng.set_mesh(m)
+    pts = np.concatenate([cases.seeds_random(20000, seed=3), m.cell_xyz[:50] * 0.999, m.vertex_xyz[:50] * 1.001])
+    got = eng.locate(pts)
+    want = P.locate(m, pts)
+    bad = np.nonzero(got != want)[0]
+    # a mismatch is only legitimate for a query equidistant (to rounding) from two centres
+    for i in bad:
+        d = np.linalg.norm(m.cell_xyz[[got[i], want[i]]] - pts[i], axis=1)
+        assert abs(d[0] - d[1]) <= 1e-6, (i, d)
+    assert bad.size <= 60  # the 50 Voronoi vertices are exact three-way ties by construction
+
+
+def _compare_traj(m, got, want, each, label):
+    n = want["status"].shape[0]
+    log_g, log_w = got["cell_log"], want["cell_log"]
+    same_log = (log_g == log_w).all(axis=1)
+    same_pos = np.array_equal(got["raw_pos"], want["raw_pos"], equal_nan=True)
+    # positions: great-circle/chord error of every recorded slot
+    err = np.linalg.norm(got["raw_pos"] - want["raw_pos"], axis=2)
+    err = np.where(np.isnan(err), 0.0, err)
+    vden = np.linalg.norm(want["raw_vel"], axis=2)
+    verr = np.linalg.norm(got["raw_vel"] - want["raw_vel"], axis=2)
+    vrel = np.where(vden > 0, verr / np.where(vden > 0, vden, 1.0), verr)
+    vrel = np.where(np.isnan(vrel), 0.0, vrel)
+    n_log_bad = int((~same_log).sum())
+    print(f"[{label}] n={n} bit-identical positions={same_pos} max|dx|={err.max():.3e} m "
+          f"max rel dv={vrel.max():.3e} cell-log mismatches={n_log_bad} "
+          f"dead ref={int((want['status'] != 0).sum())} gpu={int((got['status'] != 0).sum())}")
+    return same_log, err, vrel
+
+
+@pytest.mark.parametrize("variant,method", [("plain", "rk4"), ("rich", "rk4"), ("rich", "euler"), ("nonmono", "rk4"),
+                                            ("nonmono", "euler")])
+def test_streamline_parity(eng, P, variant, method):
+    m, s0, s1 = _setup(eng, 4, 12, variant)
+    prep = P.prepare(m, s0)
+    seeds = np.concatenate([cases.seeds_grid(15), cases.seeds_random(800, seed=5)])
+    depths = np.linspace(5.0, 2500.0, seeds.shape[0]).astype(np.float32)
+    cell0 = P.locate(m, seeds)
+    for rec in (DT, 3600):
+        want = P.streamline(m, prep, seeds, cell0, DT, DAY, rec, depths=depths, method=method)
+        got = eng.streamline(0, seeds, DT, DAY, rec, depths=depths, cell0=cell0, method=method, log_cells=True)
+        same_log, err, vrel = _compare_traj(m, got, want, DAY // rec, f"stream/{variant}/{method}/rec{rec}")
+        assert same_log.all(), "cell-id sequences must be bit-exact"
+        assert np.array_equal(got["status"], want["status"])
+        assert np.array_equal(got["steps_alive"], want["steps_alive"])
+        assert err.max() < 1e-6 and vrel.max() < 1e-9
+        assert np.abs(got["depth"] - want["depth"]).max() < 1e-3
+        # located on the device instead of given: same answer
+    got2 = eng.streamline(0, seeds, DT, DAY, 3600, depths=depths, cell0=None, method=method, log_cells=True,
+                          sort_particles=False)
+    assert np.array_equal(got2["cell_log"], got["cell_log"])
+    assert np.array_equal(got2["raw_pos"], got["raw_pos"], equal_nan=True)
+
+
+@pytest.mark.parametrize("variant,method", [("plain", "rk4"), ("rich", "rk4"), ("rich", "euler"), ("nonmono", "rk4")])
+def test_pathline_parity(eng, P, variant, method):
+    m, s0, s1 = _setup(eng, 4, 12, variant)
+    pf, pb = P.prepare(m, s0), P.prepare(m, s1)
+    seeds = np.concatenate([cases.seeds_grid(12), cases.seeds_random(600, seed=9)])
+    depths = np.linspace(50.0, 2000.0, seeds.shape[0]).astype(np.float32)
+    cell0 = P.locate(m, seeds)
+    for rec in (DT, 7200):
+        want = P.pathline(m, pf, pb, seeds, cell0, DT, DAY, rec, depths=depths, method=method)
+        got = eng.pathline(0, 1, seeds, DT, DAY, rec, depths=depths, cell0=cell0, method=method, log_cells=True)
+        same_log, err, vrel = _compare_traj(m, got, want, DAY // rec, f"path/{variant}/{method}/rec{rec}")
+        assert same_log.all()
+        assert np.array_equal(got["status"], want["status"])
+        assert err.max() < 1e-6 and vrel.max() < 1e-9
+        if s0.attrs:
+            a_g, a_w = got["raw_attr"], want["raw_attr"]
+            assert np.allclose(a_g, a_w, rtol=1e-9, atol=1e-12, equal_nan=True)
+            assert np.abs(a_w).max() > 0
+
+
+def test_backward_and_uniform_depth(eng, P):
+    m, s0, s1 = _setup(eng, 4, 12, "rich")
+    prep = P.prepare(m, s0)
+    seeds = cases.seeds_random(500, seed=21)
+    cell0 = P.locate(m, seeds)
+    want = P.streamline(m, prep, seeds, cell0, 300, 43200, 1800, depth=700.0, method="rk4", direction="backward")
+    got = eng.streamline(0, seeds, 300, 43200, 1800, depth=700.0, cell0=cell0, method="rk4", direction="backward",
+                         log_cells=True)
+    assert np.array_equal(got["cell_log"], want["cell_log"])
+    assert np.linalg.norm(got["raw_pos"] - want["raw_pos"], axis=2).max() < 1e-6
+
+
+@pytest.mark.parametrize("variant", ["plain", "rich", "nonmono"])
+def test_remap_parity(eng, P, variant):
+    m, s0, s1 = _setup(eng, 4, 12, variant)
+    prep = P.prepare(m, s0)
+    for (w, h, d) in ((90, 45, 400.0), (64, 32, 3.0), (64, 32, 6000.0), (48, 24, 0.0)):
+        want = P.remap(m, prep, w, h, depth=d)
+        got = eng.remap(0, w, h, depth=d)
+        cells_bad = int((got["pixel_cell"] != want["pixel_cell"]).sum())
+        nan_g, nan_w = np.isnan(got["img0"]), np.isnan(want["img0"])
+        print(f"[remap/{variant}/{w}x{h}/d{d}] pixel-cell mismatches={cells_bad} nan ref={int(nan_w.sum())} gpu={int(nan_g.sum())}")
+        assert cells_bad == 0
+        assert np.array_equal(nan_g, nan_w)
+        assert np.allclose(got["img0"], want["img0"], rtol=1e-9, atol=1e-12, equal_nan=True)
+        if want["img1"] is not None:
+            assert got["img1"] is not None
+            assert np.allclose(got["img1"], want["img1"], rtol=1e-9, atol=1e-9, equal_nan=True)
+        else:
+            assert got["img1"] is None
+
+
+def test_finalize_lines_matches_oracle(eng, P):
+    rng = np.random.default_rng(0)
+    n, each = 40, 6
+    seeds = rng.normal(size=(n, 3))
+    raw_pos = rng.normal(size=(n, each, 3)); raw_vel = rng.normal(size=(n, each, 3))
+    raw_pos[3, 0, 1] = np.nan; raw_pos[5, 2, 0] = np.inf; raw_pos[7, each - 1, 2] = np.nan
+    seeds[9, 0] = np.nan
+    for mode in (False, True):
+        a = eng.finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=mode)
+        b = P.finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=mode)
+        for k in ("points", "velocity", "temperature", "salinity", "last"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
