@@ -83,6 +83,14 @@ int mops_abi_version(void);
 int mops_host_alloc(void** out, size_t bytes);
 int mops_host_free(void* p);
 int mops_synchronize(mops_ctx* ctx);
+/* run the context's kernels / copies on a caller-owned cudaStream_t (e.g. torch's current
+ * stream, so that the caller's own events and NCCL calls order with them); NULL restores the
+ * context's private stream.  Snapshot uploads keep using the private side stream. */
+int mops_set_stream(mops_ctx* ctx, void* cuda_stream);
+/* CUDA-event timing marks on the context's stream: record mark `idx` (0..7) now; elapsed
+ * milliseconds between two recorded marks (synchronises on the later one). */
+int mops_mark(mops_ctx* ctx, int32_t idx);
+int mops_elapsed_ms(mops_ctx* ctx, int32_t idx_from, int32_t idx_to, double* ms_out);
 
 /* ---- mesh: replaces MOPSApp::addGrid + the per-call mesh H2D of the reference's CUDA
  *      wrappers (src/Core/MOPSApp.cpp:65-75; src/GPU/CUDA/Kernel/MPASOVisualizerKernels.cu:1369-1383).

@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "alive", 1: "bad_cell", 2: "not_in_cell", 3: "bad_column", 4:
 # every symbol include/mops_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "mops_abi_version", "mops_create", "mops_destroy", "mops_last_error", "mops_host_alloc", "mops_host_free",
-    "mops_synchronize", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait",
+    "mops_synchronize", "mops_set_stream", "mops_mark", "mops_elapsed_ms", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait",
     "mops_get_prepared", "mops_locate", "mops_streamline", "mops_pathline", "mops_finalize_lines",
     "mops_remap_fixed_depth", "mops_get_info",
 ]
@@ -88,6 +88,9 @@ def load_library():
     lib.mops_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.mops_host_free.argtypes = [vp]
     lib.mops_synchronize.argtypes = [vp]
+    lib.mops_set_stream.argtypes = [vp, vp]
+    lib.mops_mark.argtypes = [vp, i32]
+    lib.mops_elapsed_ms.argtypes = [vp, i32, i32, C.POINTER(dbl)]
     lib.mops_set_mesh.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     snap_args = [vp, i32, i32, vp, vp, vp, vp, vp, i32, C.POINTER(vp), i32]
     lib.mops_set_snapshot.argtypes = snap_args
@@ -157,6 +160,17 @@ class Engine:
 
     def synchronize(self):
         self._ck(self.lib.mops_synchronize(self.h))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._ck(self.lib.mops_set_stream(self.h, cuda_stream))
+
+    def mark(self, idx: int):
+        self._ck(self.lib.mops_mark(self.h, idx))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double(0.0)
+        self._ck(self.lib.mops_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     # ---- mesh / snapshots -------------------------------------------------------------
     def set_mesh(self, mesh):

@@ -45,7 +45,10 @@ struct Buf { // grow-only device scratch
 struct mops_ctx {
     int device = 0;
     cudaDeviceProp prop{};
-    cudaStream_t stream = nullptr, side = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr, own_stream = nullptr;
+    cudaEvent_t marks[8] = {};
+    cudaStreamAttrValue l2_attr{};
+    bool l2_attr_valid = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_kend = nullptr, ev_end = nullptr;
     std::string err;
     long long launches = 0;
@@ -587,13 +590,15 @@ int mops_create(mops_ctx** out, int device_ordinal)
         delete ctx;
         return MOPS_E_NODEVICE;
     }
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
               cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_kend) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess &&
               cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->marks[i]) == cudaSuccess;
     for (int i = 0; ok && i < MOPS_MAX_SNAPSHOT_SLOTS; ++i) {
         ok = cudaEventCreate(&ctx->snap[i].ready) == cudaSuccess && cudaEventCreate(&ctx->snap[i].last_use) == cudaSuccess;
     }
@@ -625,7 +630,8 @@ void mops_destroy(mops_ctx* ctx)
     cudaFree(ctx->d_nonmono);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
     cudaEventDestroy(ctx->ev_kend); cudaEventDestroy(ctx->ev_end);
-    cudaStreamDestroy(ctx->stream);
+    for (auto& m : ctx->marks) if (m) cudaEventDestroy(m);
+    cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->side);
     delete ctx;
 }
@@ -646,6 +652,38 @@ int mops_synchronize(mops_ctx* ctx)
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->side));
     CK(cudaStreamSynchronize(ctx->stream));
+    return MOPS_OK;
+}
+
+int mops_set_stream(mops_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (ctx->l2_attr_valid) {
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &ctx->l2_attr);
+        cudaGetLastError();
+    }
+    return MOPS_OK;
+}
+
+int mops_mark(mops_ctx* ctx, int32_t idx)
+{
+    if (!ctx || idx < 0 || idx >= 8) return MOPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->marks[idx], ctx->stream));
+    return MOPS_OK;
+}
+
+int mops_elapsed_ms(mops_ctx* ctx, int32_t idx_from, int32_t idx_to, double* ms_out)
+{
+    if (!ctx || !ms_out || idx_from < 0 || idx_from >= 8 || idx_to < 0 || idx_to >= 8) return MOPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->marks[idx_to]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->marks[idx_from], ctx->marks[idx_to]));
+    *ms_out = ms;
     return MOPS_OK;
 }
 
@@ -765,6 +803,8 @@ int mops_set_mesh(mops_ctx* ctx, int32_t n_cells, int32_t n_vertices, int32_t ma
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            ctx->l2_attr = attr;
+            ctx->l2_attr_valid = true;
         }
         cudaGetLastError();
     }
