@@ -376,13 +376,41 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
     }
 }
 
+template <int M, int MINB>
+void launch_advect_occ(mops_ctx* ctx, const AdvectParams& P, bool path)
+{
+    const int grid = blocks_for(P.n, 128);
+    if (path) k_advect<M, true, MINB><<<grid, 128, 0, ctx->stream>>>(P);
+    else k_advect<M, false, MINB><<<grid, 128, 0, ctx->stream>>>(P);
+    ctx->launches++;
+}
+
+// resident 128-thread blocks per SM the advection kernel is compiled for (register budget =
+// 65536 / (128 * MINB)); chosen from measurements on B200 (profiles/), overridable for experiments
+int advect_minb()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPS_ADVECT_MINB");
+        v = e ? atoi(e) : 3;
+        if (v < 3 || v > 6) v = 3;
+    }
+    return v;
+}
+
 template <int M>
 void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
-    const int grid = blocks_for(P.n, 128);
-    if (path) k_advect<M, true><<<grid, 128, 0, ctx->stream>>>(P);
-    else k_advect<M, false><<<grid, 128, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    if constexpr (M == 6) {
+        switch (advect_minb()) {
+        case 4: launch_advect_occ<M, 4>(ctx, P, path); return;
+        case 5: launch_advect_occ<M, 5>(ctx, P, path); return;
+        case 6: launch_advect_occ<M, 6>(ctx, P, path); return;
+        default: launch_advect_occ<M, 3>(ctx, P, path); return;
+        }
+    } else {
+        launch_advect_occ<M, (M == 8 ? 3 : 1)>(ctx, P, path);
+    }
 }
 
 int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back, const mops_traj_io* io, mops_traj_stats* stats,
@@ -498,7 +526,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     AdvectParams P;
     std::memset(&P, 0, sizeof(P));
     P.rec = ctx->rec; P.c4 = ctx->c4; P.c_int2ext = ctx->c_int2ext; P.nC = ctx->nC; P.L = F.L;
-    P.f = view_of(F); P.b = view_of(B);
+    P.sv[0] = view_of(F); P.sv[1] = view_of(B);
     P.attr_count = attr_count;
     P.use_euler = (cfg->method == MOPS_METHOD_EULER) ? 1 : 0;
     P.delta_t = (cfg->direction == MOPS_DIR_FORWARD ? 1 : -1) * (int)cfg->delta_t;

@@ -146,34 +146,25 @@ struct ZCol {
 
 // SLOW PATH (cells with a non-monotone vertex column, or non-finite weights): the reference's
 // full column with its prefix-dependent fix-up (VK:772-789), materialised in a local array
-// inside a non-inlined function so that the fast path keeps its arrays in registers.
+// inside NON-INLINED functions that recompute the weights themselves (same expressions, so
+// bit-identical) -- nothing is handed over through local memory, and the fast path keeps its
+// arrays in registers.
 template <int M>
-struct ColArgs {
-    const double* ztop;
+__device__ __forceinline__ void fill_fixed_column(const CellRec<M>* __restrict__ rec, const double* __restrict__ ztop, int L,
+                                                  double px, double py, double pz, double* col)
+{
     double w[M];
-    int vo[M];
-    int nv, L;
-};
-
-template <int M>
-__device__ __forceinline__ ColArgs<M> make_col_args(const double* ztop, const double (&w)[M], const int (&vo)[M], int nv, int L)
-{
-    ColArgs<M> a;
-    a.ztop = ztop; a.nv = nv; a.L = L;
-#pragma unroll
-    for (int i = 0; i < M; ++i) { a.w[i] = w[i]; a.vo[i] = vo[i]; }
-    return a;
-}
-
-template <int M>
-__device__ __forceinline__ void fill_fixed_column(const ColArgs<M>& a, double* col)
-{
-    for (int k = 0; k < a.L; ++k) {
+    bool wfinite;
+    const int nv = rec->nv;
+    cell_weights<M>(rec, nv, px, py, pz, w, wfinite);
+    for (int k = 0; k < L; ++k) {
         double z = 0.0;
-        for (int i = 0; i < a.nv; ++i) z += a.w[i] * a.ztop[a.vo[i] + k];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+            if (i < nv) z += w[i] * ztop[rec->vid[i] * L + k];
         col[k] = z;
     }
-    for (int k = 1; k < a.L; ++k)
+    for (int k = 1; k < L; ++k)
         if (col[k] > col[k - 1]) col[k] = col[k - 1] - 1e-9;
 }
 
@@ -217,11 +208,12 @@ struct ArrayCol {
 };
 
 template <int M>
-__device__ __noinline__ LayerRes slow_layer_stream(const ColArgs<M> a, double d)
+__device__ __noinline__ LayerRes slow_layer_stream(const CellRec<M>* __restrict__ rec, const double* __restrict__ ztop, int L,
+                                                   double px, double py, double pz, double d)
 {
     double col[100];
-    fill_fixed_column<M>(a, col);
-    return binary_layer_search(ArrayCol{col}, a.L, d);
+    fill_fixed_column<M>(rec, ztop, L, px, py, pz, col);
+    return binary_layer_search(ArrayCol{col}, L, d);
 }
 
 // `hint` (a previous answer, or < 1) is accepted only if it is the unique matching layer, in
@@ -244,12 +236,12 @@ __device__ __forceinline__ LayerRes layer_search_stream(const ZCol<M>& z, double
 // pathline layer search, VK:1182-1218: above surface -> 0 (caller reports ABOVE_SURFACE),
 // below bottom -> L-1, else the FIRST k in 1..L-1 with d <= z[k-1]+eps && d >= z[k]-eps.
 template <int M>
-__device__ __noinline__ LayerRes slow_layer_path(const ColArgs<M> a, double d)
+__device__ __noinline__ LayerRes slow_layer_path(const CellRec<M>* __restrict__ rec, const double* __restrict__ ztop, int L,
+                                                 double px, double py, double pz, double d)
 {
     double col[100];
-    fill_fixed_column<M>(a, col);
+    fill_fixed_column<M>(rec, ztop, L, px, py, pz, col);
     const double eps = 1e-8;
-    const int L = a.L;
     LayerRes r;
     r.layer = -1; r.top = 0.0; r.bot = 0.0;
     if (d > col[0] + eps) { r.layer = 0; return r; }
@@ -266,11 +258,11 @@ __device__ __noinline__ LayerRes slow_layer_path(const ColArgs<M> a, double d)
 // remap (VisualizeFixedDepth) column logic on the fixed-up column, VK:346-409.  layer = -2: depth
 // outside [z_bot - epsd, z_surf + epsd]; -1: no layer; else local_layer with top = z[max(0,l-1)].
 template <int M>
-__device__ __noinline__ LayerRes slow_layer_remap(const ColArgs<M> a, double DEPTH)
+__device__ __noinline__ LayerRes slow_layer_remap(const CellRec<M>* __restrict__ rec, const double* __restrict__ ztop, int L,
+                                                  double px, double py, double pz, double DEPTH)
 {
     double col[100];
-    fill_fixed_column<M>(a, col);
-    const int L = a.L;
+    fill_fixed_column<M>(rec, ztop, L, px, py, pz, col);
     LayerRes r;
     r.layer = -1; r.top = 0.0; r.bot = 0.0;
     double z_surf = col[0], z_bot = col[L - 1];
@@ -374,7 +366,7 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
 
     LayerRes lr;
     if (mono && wfinite) lr = layer_search_stream<M>(ZCol<M>{s.ztop, w, vo, nv, L}, depth, hint);
-    else lr = slow_layer_stream<M>(make_col_args<M>(s.ztop, w, vo, nv, L), depth);
+    else lr = slow_layer_stream<M>(rec, s.ztop, L, p.x, p.y, p.z, depth);
     const int layer = lr.layer;
     const double ztop_up = lr.top, ztop_dn = lr.bot;
     hint = layer;
@@ -400,9 +392,11 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
 }
 
 // calc_velocity_at (pathline), VK:1124-1327: front and back interpolated separately (own layer
-// search each, shared weights), blended with alpha; no zero-velocity reject.
+// search each, shared weights), blended with alpha; no zero-velocity reject.  sv[0] = front,
+// sv[1] = back; the two snapshots go through ONE copy of the code (loops kept rolled) to
+// keep the kernel's instruction footprint down.
 template <int M>
-__device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, const SnapView& f, const SnapView& b,
+__device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv,
                                          bool mono_f, bool mono_b, int L, int attr_count, const d3& p, double depth,
                                          double alpha, int& hint_f, int& hint_b, EvalOut& o)
 {
@@ -415,18 +409,25 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
 #pragma unroll
     for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
 
-    LayerRes rf, rb;
-    if (mono_f && wfinite) rf = layer_search_path<M>(ZCol<M>{f.ztop, w, vo, nv, L}, depth, hint_f);
-    else rf = slow_layer_path<M>(make_col_args<M>(f.ztop, w, vo, nv, L), depth);
-    if (mono_b && wfinite) rb = layer_search_path<M>(ZCol<M>{b.ztop, w, vo, nv, L}, depth, hint_b);
-    else rb = slow_layer_path<M>(make_col_args<M>(b.ztop, w, vo, nv, L), depth);
-    const int lf = rf.layer, lb = rb.layer;
+    // both layer searches first (VK:1182-1222) ...
+    int lf = -1, lb = -1;
+    double f_up = 0.0, f_dn = 0.0, b_up = 0.0, b_dn = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const bool mono = s ? mono_b : mono_f;
+        const int hint = s ? hint_b : hint_f;
+        LayerRes r;
+        if (mono && wfinite) r = layer_search_path<M>(ZCol<M>{sv[s].ztop, w, vo, nv, L}, depth, hint);
+        else r = slow_layer_path<M>(rec, sv[s].ztop, L, p.x, p.y, p.z, depth);
+        if (s == 0) { lf = r.layer; f_up = r.top; f_dn = r.bot; }
+        else { lb = r.layer; b_up = r.top; b_dn = r.bot; }
+    }
     if (lf == 0 || lb == 0) return ST_ABOVE_SURFACE; // the reference reads ztop[-1] here (N2)
     if (lf < 0 || lb < 0) return ST_BAD_COLUMN;
     hint_f = lf;
     hint_b = lb;
-    const double f_up = rf.top, f_dn = rf.bot, b_up = rb.top, b_dn = rb.bot;
 
+    // ... then denominators (front, back: VK:1229-1241) ...
     double mn = (f_up < depth) ? f_up : depth;
     const double x_front = (f_dn < mn) ? mn : f_dn;
     const double denom_front = f_up - f_dn;
@@ -438,36 +439,38 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
     if (fabs(denom_back) < 1e-12) return ST_BAD_COLUMN;
     const double t_back = (x_back - b_dn) / denom_back;
 
-    double dx, dy, dz, dw, ux, uy, uz, uw;
-    gather_velw<M>(f.velw, vo, w, nv, lf, dx, dy, dz, dw);
-    gather_velw<M>(f.velw, vo, w, nv, lf - 1, ux, uy, uz, uw);
-    const double omf = 1.0 - t_front;
-    const double ffx = t_front * ux + omf * dx, ffy = t_front * uy + omf * dy, ffz = t_front * uz + omf * dz;
-    const double w_front = t_front * uw + omf * dw;
-    gather_velw<M>(b.velw, vo, w, nv, lb, dx, dy, dz, dw);
-    gather_velw<M>(b.velw, vo, w, nv, lb - 1, ux, uy, uz, uw);
-    const double omb = 1.0 - t_back;
-    const double bbx = t_back * ux + omb * dx, bby = t_back * uy + omb * dy, bbz = t_back * uz + omb * dz;
-    const double w_back = t_back * uw + omb * dw;
+    // ... then the gathers and the alpha blend (VK:1243-1324)
     const double oma = 1.0 - alpha;
-    o.hx = alpha * bbx + oma * ffx; // VK:1259
-    o.hy = alpha * bby + oma * ffy;
-    o.hz = alpha * bbz + oma * ffz;
-    o.vv = alpha * w_back + oma * w_front; // VK:1286
-    o.a0 = 0.0; o.a1 = 0.0;
-    if (attr_count >= 1) { // VK:1288-1306
-        const double adf = gather_scalar<M>(f.attr0, vo, w, nv, lf), auf = gather_scalar<M>(f.attr0, vo, w, nv, lf - 1);
-        const double a_front = t_front * auf + omf * adf;
-        const double adb = gather_scalar<M>(b.attr0, vo, w, nv, lb), aub = gather_scalar<M>(b.attr0, vo, w, nv, lb - 1);
-        const double a_back = t_back * aub + omb * adb;
-        o.a0 = alpha * a_back + oma * a_front;
-    }
-    if (attr_count >= 2) { // VK:1307-1323
-        const double adf = gather_scalar<M>(f.attr1, vo, w, nv, lf), auf = gather_scalar<M>(f.attr1, vo, w, nv, lf - 1);
-        const double a_front = t_front * auf + omf * adf;
-        const double adb = gather_scalar<M>(b.attr1, vo, w, nv, lb), aub = gather_scalar<M>(b.attr1, vo, w, nv, lb - 1);
-        const double a_back = t_back * aub + omb * adb;
-        o.a1 = alpha * a_back + oma * a_front;
+    double ffx = 0.0, ffy = 0.0, ffz = 0.0, ffw = 0.0, fa0 = 0.0, fa1 = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int layer = s ? lb : lf;
+        const double t = s ? t_back : t_front;
+        const double omt = 1.0 - t;
+        double dx, dy, dz, dw, ux, uy, uz, uw;
+        gather_velw<M>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw);
+        gather_velw<M>(sv[s].velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
+        const double vx = t * ux + omt * dx, vy = t * uy + omt * dy, vz = t * uz + omt * dz;
+        const double vw = t * uw + omt * dw;
+        double a0 = 0.0, a1 = 0.0;
+        if (attr_count >= 1) {
+            const double ad = gather_scalar<M>(sv[s].attr0, vo, w, nv, layer), au = gather_scalar<M>(sv[s].attr0, vo, w, nv, layer - 1);
+            a0 = t * au + omt * ad;
+        }
+        if (attr_count >= 2) {
+            const double ad = gather_scalar<M>(sv[s].attr1, vo, w, nv, layer), au = gather_scalar<M>(sv[s].attr1, vo, w, nv, layer - 1);
+            a1 = t * au + omt * ad;
+        }
+        if (s == 0) {
+            ffx = vx; ffy = vy; ffz = vz; ffw = vw; fa0 = a0; fa1 = a1;
+        } else {
+            o.hx = alpha * vx + oma * ffx; // VK:1259
+            o.hy = alpha * vy + oma * ffy;
+            o.hz = alpha * vz + oma * ffz;
+            o.vv = alpha * vw + oma * ffw; // VK:1286
+            o.a0 = (attr_count >= 1) ? alpha * a0 + oma * fa0 : 0.0;
+            o.a1 = (attr_count >= 2) ? alpha * a1 + oma * fa1 : 0.0;
+        }
     }
     return ST_ALIVE;
 }

@@ -317,7 +317,7 @@ struct AdvectParams {
     const double4* c4;
     const int* c_int2ext;
     int nC, L;
-    SnapView f, b;
+    SnapView sv[2];   // [0] front, [1] back (pathline)
     int attr_count;   // pathline attributes in use (0..2)
     int use_euler;
     int delta_t;      // signed seconds
@@ -348,8 +348,8 @@ __device__ __forceinline__ void st3(double* p, long long i, double x, double y, 
 
 __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : ((1.0 < v) ? 1.0 : v); }
 
-template <int M, bool PATH>
-__global__ void __launch_bounds__(128) k_advect(const AdvectParams P)
+template <int M, bool PATH, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
 {
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0, my_alive = 0;
@@ -404,8 +404,8 @@ __global__ void __launch_bounds__(128) k_advect(const AdvectParams P)
                 if (P.cell_log) P.cell_log[pid * (long long)P.times + step] = P.c_int2ext[cell];
 
                 const CellRec<M>* __restrict__ rec = recs + cell;
-                const bool mono_f = P.f.mono[cell] != 0;
-                const bool mono_b = PATH ? (P.b.mono[cell] != 0) : false;
+                const bool mono_f = P.sv[0].mono[cell] != 0;
+                const bool mono_b = PATH ? (P.sv[1].mono[cell] != 0) : false;
                 const double cur_depth = -1.0 * (double)depth_f;
                 const double alpha = PATH ? (double)step / (double)P.times : 0.0; // VK:1345
                 const double r = len3(pos);
@@ -414,43 +414,40 @@ __global__ void __launch_bounds__(128) k_advect(const AdvectParams P)
                 d3 new_pos;
                 EvalOut o;
 
+                // Euler = one stage, RK4 = four; all stages against the start-of-step cell
+                // (VK:931-957, R1).  One rolled loop => one inlined copy of the evaluation.
+                const int n_stage = P.use_euler ? 1 : 4;
+                d3 hprev = mk3(0.0, 0.0, 0.0);
+                int st = ST_ALIVE;
+#pragma unroll 1
+                for (int s = 0; s < n_stage; ++s) {
+                    d3 p = pos;
+                    double a_s = alpha;
+                    if (s > 0) {
+                        p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5);
+                        if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
+                    }
+                    st = PATH ? eval_path<M>(rec, P.sv, mono_f, mono_b, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                              : eval_stream<M>(rec, P.sv[0], mono_f, P.L, p, cur_depth, hint_f, o);
+                    if (st != ST_ALIVE) break;
+                    if (s == 0) {
+                        hvel = mk3(o.hx, o.hy, o.hz);
+                        vvel = o.vv; at0 = o.a0; at1 = o.a1;
+                    } else {
+                        const double c = (s == 3) ? 1.0 : 2.0; // s1 + 2 s2 + 2 s3 + s4, left to right (VK:959-960)
+                        hvel.x = hvel.x + c * o.hx;
+                        hvel.y = hvel.y + c * o.hy;
+                        hvel.z = hvel.z + c * o.hz;
+                        vvel = vvel + c * o.vv;
+                        at0 = at0 + c * o.a0;
+                        at1 = at1 + c * o.a1;
+                    }
+                    hprev = mk3(o.hx, o.hy, o.hz);
+                }
+                if (st != ST_ALIVE) { status = st; break; }
                 if (P.use_euler) {
-                    const int st = PATH ? eval_path<M>(rec, P.f, P.b, mono_f, mono_b, P.L, P.attr_count, pos, cur_depth, alpha, hint_f, hint_b, o)
-                                        : eval_stream<M>(rec, P.f, mono_f, P.L, pos, cur_depth, hint_f, o);
-                    if (st != ST_ALIVE) { status = st; break; }
-                    hvel = mk3(o.hx, o.hy, o.hz);
-                    vvel = o.vv; at0 = o.a0; at1 = o.a1;
                     new_pos = rotate_euler(pos, hvel, P.delta_t, r); // VK:968-972
                 } else {
-                    // RK4: all four stages against the start-of-step cell (VK:939-957, R1)
-                    d3 hprev = mk3(0.0, 0.0, 0.0);
-                    int st = ST_ALIVE;
-#pragma unroll 1
-                    for (int s = 0; s < 4; ++s) {
-                        d3 p = pos;
-                        double a_s = alpha;
-                        if (s > 0) {
-                            p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5);
-                            if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
-                        }
-                        st = PATH ? eval_path<M>(rec, P.f, P.b, mono_f, mono_b, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
-                                  : eval_stream<M>(rec, P.f, mono_f, P.L, p, cur_depth, hint_f, o);
-                        if (st != ST_ALIVE) break;
-                        if (s == 0) {
-                            hvel = mk3(o.hx, o.hy, o.hz);
-                            vvel = o.vv; at0 = o.a0; at1 = o.a1;
-                        } else {
-                            const double c = (s == 3) ? 1.0 : 2.0; // s1 + 2 s2 + 2 s3 + s4, left to right (VK:959-960)
-                            hvel.x = hvel.x + c * o.hx;
-                            hvel.y = hvel.y + c * o.hy;
-                            hvel.z = hvel.z + c * o.hz;
-                            vvel = vvel + c * o.vv;
-                            at0 = at0 + c * o.a0;
-                            at1 = at1 + c * o.a1;
-                        }
-                        hprev = mk3(o.hx, o.hy, o.hz);
-                    }
-                    if (st != ST_ALIVE) { status = st; break; }
                     hvel.x = hvel.x / 6.0; hvel.y = hvel.y / 6.0; hvel.z = hvel.z / 6.0;
                     vvel = vvel / 6.0;
                     at0 = at0 / 6.0; at1 = at1 / 6.0;
@@ -603,7 +600,7 @@ __global__ void __launch_bounds__(128) k_remap(const RemapParams P)
                     }
                 }
             } else {
-                const LayerRes lr = slow_layer_remap<M>(make_col_args<M>(P.s.ztop, w, vo, nv, L), DEPTH);
+                const LayerRes lr = slow_layer_remap<M>(rec, P.s.ztop, L, pos.x, pos.y, pos.z, DEPTH);
                 local_layer = lr.layer; topI = lr.top; botI = lr.bot;
                 if (lr.layer == -2) { ok = false; local_layer = -1; }
             }

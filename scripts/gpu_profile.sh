@@ -1,0 +1,8 @@
+set -x
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+tail -3 gpurun_out/plain.log | cut -c1-400
+ncu --set full --clock-control none --import-source on -k regex:k_advect -s 3 -c 1 -f -o gpurun_out/prof_advect $CMD > gpurun_out/ncu_full.log 2>&1
+tail -5 gpurun_out/ncu_full.log
+ls -la gpurun_out/
