@@ -259,13 +259,8 @@ def main():
     # seeds: uniform on the sphere |lat| < 80 deg, rank r keeps its longitude sector
     n_total = args.particles
     seeds_all = S.uniform_sphere_seeds(n_total, 20261018 + 5)
-    if world > 1:
-        lon = np.arctan2(seeds_all[:, 1], seeds_all[:, 0])
-        sector = np.minimum(((lon + np.pi) / (2 * np.pi) * world).astype(np.int64), world - 1)
-        seeds_np = np.ascontiguousarray(seeds_all[sector == rank])
-        del lon, sector
-    else:
-        seeds_np = seeds_all
+    from mops_b200 import sharding
+    seeds_np, _global_idx = sharding.shard_seeds(seeds_all, rank, world)
     del seeds_all
     n = seeds_np.shape[0]
     each = 2
@@ -278,11 +273,7 @@ def main():
     out_vel = torch.empty((n, each, 3), dtype=torch.float64, device=dev)
     cfg = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, 0 if args.no_sort else 1)
     io = capi.TrajIO(n, xyz.data_ptr(), depth.data_ptr(), None, out_pos.data_ptr(), out_vel.data_ptr(), None, None, None, None, None)
-    gather_buf = [torch.empty((0,), device=dev)]
-    if world > 1:
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
-        counts = [int(c.item()) for c in counts]
+    counts = sharding.all_counts(n, world, device=dev)
     setup_s = time.perf_counter() - t_setup
 
     def one_step(i, io_, cfg_):
@@ -291,11 +282,7 @@ def main():
         st = eng.traj_device(True, (i % 3, (i + 1) % 3), cfg_, io_, want_stats=True)
         if world > 1:
             # the one exchange of the path: end points gathered to rank 0 over NCCL/NVLink
-            if rank == 0:
-                glist = [torch.empty((c, 3), dtype=torch.float64, device=dev) for c in counts]
-                dist.gather(xyz, glist, dst=0)
-            else:
-                dist.gather(xyz, None, dst=0)
+            sharding.gather_rows(xyz, counts, rank, world, dst=0)
         return st
 
     def barrier():

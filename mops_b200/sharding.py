@@ -1,0 +1,68 @@
+"""Particle sharding for the multi-GPU path: particles are independent, the mesh
+and the resident snapshots are replicated on every GPU, each rank owns a spatially compact
+block of particles (a longitude sector), and the only exchange is the gather of results to
+rank 0 at the end of an interval.  Host-side logic only (torch.distributed does the plumbing:
+NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def longitude_sector(xyz: np.ndarray, world: int) -> np.ndarray:
+    """sector id in [0, world) of every particle: equal-width longitude wedges"""
+    lon = np.arctan2(xyz[:, 1], xyz[:, 0])
+    return np.minimum(((lon + np.pi) / (2.0 * np.pi) * world).astype(np.int64), world - 1)
+
+
+def shard_seeds(xyz: np.ndarray, rank: int, world: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(local seeds, their indices in the global seed array); world == 1 keeps everything"""
+    if world <= 1:
+        return xyz, np.arange(xyz.shape[0], dtype=np.int64)
+    idx = np.nonzero(longitude_sector(xyz, world) == rank)[0]
+    return np.ascontiguousarray(xyz[idx]), idx
+
+
+def all_counts(n_local: int, world: int, device=None) -> List[int]:
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return [n_local]
+    t = torch.tensor([n_local], dtype=torch.int64, device=device)
+    out = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [int(c.item()) for c in out]
+
+
+def gather_rows(local, counts: List[int], rank: int, world: int, dst: int = 0):
+    """gather a [n_local, k] tensor of every rank to `dst`; n_local may differ between ranks
+    (gather collectives need equal shapes, so shards are padded to the largest and sliced on
+    arrival).  Returns the list of per-rank tensors on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return [local]
+    cmax = max(counts)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == cmax:
+        padded = local.contiguous()
+    else:
+        padded = torch.empty((cmax,) + tail, dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]].copy_(local)
+    if rank == dst:
+        bufs = [torch.empty((cmax,) + tail, dtype=local.dtype, device=local.device) for _ in counts]
+        dist.gather(padded, bufs, dst=dst)
+        return [b[:c] for b, c in zip(bufs, counts)]
+    dist.gather(padded, None, dst=dst)
+    return None
+
+
+def scatter_back(global_n: int, parts, indices: List[np.ndarray]) -> np.ndarray:
+    """reassemble gathered per-rank rows into caller (global seed) order"""
+    import torch
+    first = parts[0]
+    out = np.empty((global_n,) + tuple(first.shape[1:]), dtype=first.cpu().numpy().dtype)
+    for p, idx in zip(parts, indices):
+        out[idx] = p.cpu().numpy()
+    return out

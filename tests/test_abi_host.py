@@ -1,0 +1,94 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/mops_b200.h declares, fails
+loudly without a GPU (no fallback), and its pure-host function matches the reference's NaN
+trimming cases (test/test_trajector.cpp)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from mops_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return capi.load_library(), capi
+
+
+def test_exports_match_header():
+    lib, capi = _lib()
+    hdr = open(os.path.join(ROOT, "include", "mops_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|void|const char\*)\s+(mops_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert declared == set(capi.ABI_SYMBOLS), declared ^ set(capi.ABI_SYMBOLS)
+    raw = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert raw.mops_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    lib, capi = _lib()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.MopsError):
+        capi.Engine(0)
+    h = ctypes.c_void_p()
+    assert lib.mops_create(ctypes.byref(h), 0) == -3  # MOPS_E_NODEVICE
+    assert not h.value
+
+
+def test_product_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under mops_b200/ or include/ may name it"""
+    for top in ("mops_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".sh")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read().lower()
+                    assert "oracle" not in txt, f"{os.path.join(dirpath, f)} mentions the oracle"
+
+
+def _finalize(capi, seeds, raw_pos, raw_vel, mode):
+    lib = capi.load_library()
+    n, each = raw_pos.shape[:2]
+    per = each + 1
+    pts = np.zeros((n, per, 3)); vel = np.zeros((n, per, 3)); t = np.zeros((n, per)); s = np.zeros((n, per)); last = np.zeros((n, 3))
+    rc = lib.mops_finalize_lines(n, each, seeds.ctypes.data, raw_pos.ctypes.data, raw_vel.ctypes.data, mode, pts.ctypes.data,
+                                 vel.ctypes.data, t.ctypes.data, s.ctypes.data, last.ctypes.data)
+    assert rc == 0
+    return pts, vel, t, s, last
+
+
+def test_nan_trimming_cases_of_reference_test():
+    """the four sections of test/test_trajector.cpp:27-208, on the flat form"""
+    lib, capi = _lib()
+    nan = np.nan
+    each = 4
+    seeds = np.array([[nan, 0, 0], [1.0, 1, 1], [2.0, 2, 2], [3.0, 3, 3]])
+    raw_pos = np.arange(4 * each * 3, dtype=np.float64).reshape(4, each, 3) + 10.0
+    raw_vel = np.ones((4, each, 3))
+    raw_pos[1, 0, 0] = nan      # NaN at index 1 of the assembled line
+    raw_pos[2, 2, 1] = nan      # NaN mid-line (assembled index 3)
+    pts, vel, t, s, last = _finalize(capi, seeds, raw_pos, raw_vel, 0)
+    per = each + 1
+    # (1) first point NaN: whole line = first point, velocities zero, length preserved
+    assert np.isnan(pts[0, :, 0]).all() and (vel[0] == 0).all() and pts.shape[1] == per
+    # (2) NaN at index 1: padded with point 0; velocities zero from index 0 on
+    assert (pts[1] == seeds[1]).all() and (vel[1] == 0).all() and (last[1] == seeds[1]).all()
+    # (3) NaN mid-line at k=3: points 3.. = point 2; velocity zero from k-1 = 2 on, earlier kept
+    assert (pts[2, 3:] == pts[2, 2]).all() and (vel[2, 2:] == 0).all() and (vel[2, :2] == 1).all()
+    assert (last[2] == pts[2, 2]).all()
+    # (4) all valid: untouched; velocity has the trailing zero pad (R7)
+    assert (pts[3, 0] == seeds[3]).all() and (pts[3, 1:] == raw_pos[3]).all()
+    assert (vel[3, :each] == 1).all() and (vel[3, each] == 0).all() and (last[3] == raw_pos[3, -1]).all()
+    # oracle restatement agrees bit for bit, both modes
+    from oracle import port_oracle as P
+    for mode in (0, 1):
+        a = _finalize(capi, seeds, raw_pos, raw_vel, mode)
+        b = P.finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=bool(mode))
+        for x, k in zip(a, ("points", "velocity", "temperature", "salinity", "last")):
+            assert np.array_equal(x, b[k], equal_nan=True), k
