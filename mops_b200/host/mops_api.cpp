@@ -1,0 +1,615 @@
+// mops_api.cpp -- host side of the C++ drop-in (include/api/MOPS.h) over the C ABI
+// (include/mops_b200.h).  Mirrors the call sequence and error behaviour of the reference's
+// src/Core/MOPS.cpp:10-127 and src/Core/MOPSApp.cpp:34-337; every compute step is a C-ABI call
+// into libmops_b200.so (CUDA kernels) -- there is no host implementation of the path here.
+#include "api/MOPS.h"
+#include "mops_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+
+namespace MOPS {
+
+// =================================================================================================
+// timing: the five getters of the reference API (src/Utils/Timer.hpp:17-25, 56-264), fed with
+// CUDA-event times reported by the engine plus host wall time of each API call
+// =================================================================================================
+namespace {
+const char* kCategories[] = {"IO_Read", "IO_Write", "Preprocessing", "MemoryCopy", "GPUKernel", "CPUCompute", "Other"};
+struct TimerEntry {
+    std::string name;
+    int category;
+    double ms;
+};
+struct TimerBook {
+    std::mutex mu;
+    std::vector<TimerEntry> entries;
+    void add(const std::string& name, int cat, double ms)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        entries.push_back({name, cat, ms});
+    }
+    double category(int cat)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        double s = 0.0;
+        for (auto& e : entries)
+            if (e.category == cat) s += e.ms;
+        return s;
+    }
+};
+TimerBook& book()
+{
+    static TimerBook b;
+    return b;
+}
+int category_index(const char* c)
+{
+    for (int i = 0; i < 6; ++i)
+        if (std::strcmp(c, kCategories[i]) == 0) return i;
+    return 6; // anything else is booked as "Other", as the reference does (src/Core/MOPS.cpp:103-118)
+}
+struct Scope {
+    std::string name;
+    int cat;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    Scope(std::string n, int c) : name(std::move(n)), cat(c) {}
+    ~Scope() { book().add(name, cat, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
+void engine_error(::mops_ctx* c, const char* where, int rc)
+{
+    std::fprintf(stderr, "[MOPS/b200]::%s failed (%d): %s\n", where, rc, c ? mops_last_error(c) : "no context");
+}
+} // namespace
+
+// =================================================================================================
+// data model setters (src/Core/MPASOGrid.cpp:82-186, src/Core/MPASOSolution.cpp:1150-1210)
+// =================================================================================================
+void MPASOGrid::setGridAttribute(GridAttributeType type, int val)
+{
+    switch (type) {
+    case GridAttributeType::kCellSize: mCellsSize = val; break;
+    case GridAttributeType::kEdgeSize: mEdgesSize = val; break;
+    case GridAttributeType::kVertexSize: mVertexSize = val; break;
+    case GridAttributeType::kMaxEdgesSize: mMaxEdgesSize = val; break;
+    case GridAttributeType::kVertLevels: mVertLevels = val; break;
+    case GridAttributeType::kVertLevelsP1: mVertLevelsP1 = val; break;
+    default: std::cout << "[MPASOGrid]::Invalid GridAttributeType" << std::endl; break;
+    }
+}
+void MPASOGrid::setGridAttributesVec3(GridAttributeType type, const std::vector<vec3>& vec)
+{
+    switch (type) {
+    case GridAttributeType::kVertexCoord: vertexCoord_vec = vec; break;
+    case GridAttributeType::kCellCoord: cellCoord_vec = vec; break;
+    case GridAttributeType::kEdgeCoord: edgeCoord_vec = vec; break;
+    default: std::cout << "Error: Invalid GridAttributeType" << std::endl;
+    }
+}
+void MPASOGrid::setGridAttributesVec2(GridAttributeType type, const std::vector<vec2>& vec)
+{
+    if (type == GridAttributeType::kVertexLatLon) vertexLatLon_vec = vec;
+    else std::cout << "Error: Invalid GridAttributeType" << std::endl;
+}
+void MPASOGrid::setGridAttributesInt(GridAttributeType type, const std::vector<size_t>& vec)
+{
+    switch (type) {
+    case GridAttributeType::kVerticesOnCell: verticesOnCell_vec = vec; break;
+    case GridAttributeType::kVerticesOnEdge: verticesOnEdge_vec = vec; break;
+    case GridAttributeType::kCellsOnVertex: cellsOnVertex_vec = vec; break;
+    case GridAttributeType::kCellsOnCell: cellsOnCell_vec = vec; break;
+    case GridAttributeType::kNumberVertexOnCell: numberVertexOnCell_vec = vec; break;
+    case GridAttributeType::kCellsOnEdge: cellsOnEdge_vec = vec; break;
+    case GridAttributeType::kEdgesOnCell: edgesOnCell_vec = vec; break;
+    default: std::cout << "Error: Invalid GridAttributeType" << std::endl;
+    }
+}
+void MPASOGrid::setGridAttributesFloat(GridAttributeType type, const std::vector<float>& vec)
+{
+    if (type == GridAttributeType::kCellWeight) cellWeight_vec = vec;
+    else std::cout << "Error: Invalid GridAttributeType" << std::endl;
+}
+bool MPASOGrid::checkAttribute()
+{
+    // the reference's checks that matter for the hot path (src/Core/MPASOGrid.cpp:516-598)
+    auto bad = [](const char* what) { std::cout << "[MPASOGrid]::Error: " << what << " is not set" << std::endl; return false; };
+    if (mCellsSize == 0) return bad("mCellsSize");
+    if (mVertexSize == 0) return bad("mVertexSize");
+    if (mMaxEdgesSize == 0) return bad("mMaxEdgesSize");
+    if (mVertLevels == 0) return bad("mVertLevels");
+    if (mVertLevelsP1 == 0) return bad("mVertLevelsP1");
+    if (cellCoord_vec.empty()) return bad("cellCoord_vec");
+    if (vertexCoord_vec.empty()) return bad("vertexCoord_vec");
+    if (verticesOnCell_vec.empty()) return bad("verticesOnCell_vec");
+    if (cellsOnVertex_vec.empty()) return bad("cellsOnVertex_vec");
+    if (cellsOnCell_vec.empty()) return bad("cellsOnCell_vec");
+    if (numberVertexOnCell_vec.empty()) return bad("numberVertexOnCell_vec");
+    return true;
+}
+
+void MPASOSolution::setAttribute(GridAttributeType type, int val)
+{
+    switch (type) {
+    case GridAttributeType::kCellSize: mCellsSize = val; break;
+    case GridAttributeType::kEdgeSize: mEdgesSize = val; break;
+    case GridAttributeType::kVertexSize: mVertexSize = val; break;
+    case GridAttributeType::kMaxEdgesSize: mMaxEdgesSize = val; break;
+    case GridAttributeType::kVertLevels: mVertLevels = val; break;
+    case GridAttributeType::kVertLevelsP1: mVertLevelsP1 = val; break;
+    default: std::cerr << "[Error]: Invalid GridAttributeType" << std::endl; break;
+    }
+}
+void MPASOSolution::setAttributesDouble(AttributeType type, const std::vector<double>& vec)
+{
+    switch (type) {
+    case AttributeType::kZTop: cellZTop_vec = vec; break;
+    case AttributeType::kLayerThickness: cellLayerThickness_vec = vec; break;
+    case AttributeType::kBottomDepth: cellBottomDepth_vec = vec; break;
+    case AttributeType::kZonalVelocity: cellZonalVelocity_vec = vec; break;
+    case AttributeType::kMeridionalVelocity: cellMeridionalVelocity_vec = vec; break;
+    case AttributeType::kNormalVelocity: cellNormalVelocity_vec = vec; break;
+    default: std::cerr << "[Error]: Invalid AttributeType" << std::endl; break;
+    }
+}
+int MPASOSolution::getID() const
+{
+    const std::string key = mTimeStamp + "_" + std::to_string(mTimesteps);
+    uint32_t h = 2166136261u;
+    for (unsigned char ch : key) h = (h ^ ch) * 16777619u;
+    return static_cast<int>(h);
+}
+bool MPASOSolution::checkAttribute()
+{
+    if (cellZTop_vec.empty() && cellLayerThickness_vec.empty()) { // src/Core/MPASOSolution.cpp:1222-1226
+        std::cerr << "[MPASOSolution]::Error: Invalid ZTop Attribute" << std::endl;
+        return false;
+    }
+    return true;
+}
+
+void MPASOField::calcInWhichCells(std::vector<CartesianCoord>& points_vec, std::vector<int>& cell_id_vec)
+{
+    app.locate(points_vec, cell_id_vec);
+}
+
+// =================================================================================================
+// MOPSApp
+// =================================================================================================
+MOPSApp app;
+
+MOPSApp::MOPSApp() = default;
+MOPSApp::~MOPSApp()
+{
+    if (mCtx) mops_destroy(mCtx);
+}
+
+void MOPSApp::init(const char* device)
+{
+    std::cout << " [ system information ]\n";
+    if (device && std::strcmp(device, "cpu") == 0)
+        std::cout << "Device requested: cpu -- this build has no CPU path; using the CUDA device\n";
+    int dev = 0;
+    if (const char* e = std::getenv("MOPS_DEVICE")) dev = std::atoi(e);
+    if (!mCtx) {
+        const int rc = mops_create(&mCtx, dev);
+        if (rc != MOPS_OK) {
+            std::cerr << " [ MOPS: no usable CUDA device (mops_create -> " << rc << "); there is no CPU fallback ]\n";
+            std::exit(1);
+        }
+    }
+    mops_info info;
+    mops_get_info(mCtx, &info);
+    std::cout << "Device selected : CUDA device " << info.device << " (sm_" << info.cc_major << info.cc_minor << ", " << info.sm_count
+              << " SMs) -- B200-native engine\n";
+    std::cout << "MOPS Version    : mops-b200 (ABI " << mops_abi_version() << ")\n";
+    mpasoGrid = std::make_shared<MPASOGrid>();
+}
+
+void MOPSApp::addGrid(std::shared_ptr<MPASOGrid> grid)
+{
+    Scope sc("Preprocessing::addGrid", 2);
+    mpasoGrid = std::move(grid);
+    if (!mCtx) {
+        std::cerr << " [ MOPS is not initialised: call MOPS_Init first ]\n";
+        std::exit(1);
+    }
+    const MPASOGrid& g = *mpasoGrid;
+    const size_t nC = static_cast<size_t>(g.mCellsSize), nV = static_cast<size_t>(g.mVertexSize), E = static_cast<size_t>(g.mMaxEdgesSize);
+    if (g.cellCoord_vec.size() < nC || g.vertexCoord_vec.size() < nV || g.verticesOnCell_vec.size() < nC * E ||
+        g.cellsOnCell_vec.size() < nC * E || g.cellsOnVertex_vec.size() < nV * 3 || g.numberVertexOnCell_vec.size() < nC) {
+        std::cerr << "[MOPSApp]::addGrid: grid arrays are smaller than the declared sizes\n";
+        std::exit(1);
+    }
+    auto narrow = [](const std::vector<size_t>& v, size_t n) {
+        std::vector<int32_t> o(n);
+        for (size_t i = 0; i < n; ++i) o[i] = static_cast<int32_t>(v[i]);
+        return o;
+    };
+    const auto voc = narrow(g.verticesOnCell_vec, nC * E), coc = narrow(g.cellsOnCell_vec, nC * E),
+               cov = narrow(g.cellsOnVertex_vec, nV * 3), ne = narrow(g.numberVertexOnCell_vec, nC);
+    const int rc = mops_set_mesh(mCtx, g.mCellsSize, g.mVertexSize, g.mMaxEdgesSize, reinterpret_cast<const double*>(g.cellCoord_vec.data()),
+                                 reinterpret_cast<const double*>(g.vertexCoord_vec.data()), voc.data(), coc.data(), cov.data(), ne.data());
+    if (rc != MOPS_OK) {
+        engine_error(mCtx, "addGrid", rc);
+        std::exit(1);
+    }
+    mSlotOf.clear();
+    mSlotOrder.clear();
+}
+
+void MOPSApp::addSol(int solID, std::shared_ptr<MPASOSolution> sol)
+{
+    Scope sc("Preprocessing::addSol", 2);
+    if (mpasoAttributeMap.count(solID)) return; // a repeated solID is ignored (src/Core/MOPSApp.cpp:82-87)
+    sol->mCellsSize = mpasoGrid->mCellsSize;
+    sol->mEdgesSize = mpasoGrid->mEdgesSize;
+    sol->mMaxEdgesSize = mpasoGrid->mMaxEdgesSize;
+    sol->mVertexSize = mpasoGrid->mVertexSize;
+    mpasoGrid->mVertLevels = sol->mVertLevels;
+    mpasoGrid->mVertLevelsP1 = sol->mVertLevelsP1;
+    sol->mTotalZTopLayer = sol->mVertLevels;
+    sol->mTotalZTopLayerP1 = sol->mVertLevels + 1;
+    mpasoAttributeMap[solID] = std::move(sol);
+    // the preprocessing chain of the reference (src/Core/MOPSApp.cpp:100-130) runs on the device
+    // when the snapshot becomes resident (residentSlot), not on the host here
+}
+
+void MOPSApp::addField()
+{
+    mpasoField = std::make_shared<MPASOField>();
+    mpasoField->mGrid = mpasoGrid;
+    mpasoField->mSol_Front = mpasoAttributeMap.begin()->second;
+    mFrontID = mpasoAttributeMap.begin()->first;
+    mHasBack = false;
+}
+
+// make `solID` resident in one of the engine's snapshot slots (LRU over MOPS_MAX_SNAPSHOT_SLOTS)
+int MOPSApp::residentSlot(int solID)
+{
+    auto touch = [&](int slot) {
+        for (size_t i = 0; i < mSlotOrder.size(); ++i)
+            if (mSlotOrder[i] == slot) { mSlotOrder.erase(mSlotOrder.begin() + i); break; }
+        mSlotOrder.push_back(slot);
+    };
+    auto it = mSlotOf.find(solID);
+    if (it != mSlotOf.end()) {
+        touch(it->second);
+        return it->second;
+    }
+    int slot = -1;
+    if (static_cast<int>(mSlotOf.size()) < MOPS_MAX_SNAPSHOT_SLOTS) {
+        std::vector<bool> used(MOPS_MAX_SNAPSHOT_SLOTS, false);
+        for (auto& kv : mSlotOf) used[kv.second] = true;
+        for (int s = 0; s < MOPS_MAX_SNAPSHOT_SLOTS; ++s)
+            if (!used[s]) { slot = s; break; }
+    } else {
+        slot = mSlotOrder.front();
+        for (auto kv = mSlotOf.begin(); kv != mSlotOf.end(); ++kv)
+            if (kv->second == slot) { mSlotOf.erase(kv); break; }
+    }
+    const MPASOSolution& s = *mpasoAttributeMap.at(solID);
+    const size_t nC = static_cast<size_t>(mpasoGrid->mCellsSize), L = static_cast<size_t>(s.mVertLevels);
+    if (s.cellZonalVelocity_vec.size() < nC * L || s.cellMeridionalVelocity_vec.size() < nC * L ||
+        s.cellLayerThickness_vec.size() < nC * L || s.cellBottomDepth_vec.size() < nC) {
+        std::cerr << "[MOPSApp]::solution " << solID << ": zonal/meridional velocity, layerThickness and bottomDepth are required\n";
+        std::exit(1);
+    }
+    // scalar attributes in std::map (alphabetical) order, first two (R11)
+    std::vector<const double*> attrs;
+    for (auto& kv : s.mDoubleAttributes) {
+        if (attrs.size() >= MOPS_MAX_ATTRS) break;
+        if (kv.second.size() >= nC * L) attrs.push_back(kv.second.data());
+    }
+    const double* wtop = s.cellVertVelocity_vec.size() >= nC * (L + 1) ? s.cellVertVelocity_vec.data() : nullptr;
+    Scope sc("Preprocessing::snapshot", 2);
+    const int rc = mops_set_snapshot(mCtx, slot, s.mVertLevels, s.cellZonalVelocity_vec.data(), s.cellMeridionalVelocity_vec.data(),
+                                     s.cellLayerThickness_vec.data(), s.cellBottomDepth_vec.data(), wtop, static_cast<int>(attrs.size()),
+                                     attrs.empty() ? nullptr : attrs.data(), static_cast<int>(s.mDoubleAttributes.size()));
+    if (rc != MOPS_OK) {
+        engine_error(mCtx, "set_snapshot", rc);
+        std::exit(1);
+    }
+    mSlotOf[solID] = slot;
+    touch(slot);
+    return slot;
+}
+
+void MOPSApp::activeAttribute(int ID1, std::optional<int> ID2)
+{
+    mpasoField = std::make_shared<MPASOField>();
+    auto it = mpasoAttributeMap.find(ID1);
+    if (it == mpasoAttributeMap.end()) {
+        std::fprintf(stderr, "[MOPSApp]::activeAttribute: solID %d not found\n", ID1);
+        return;
+    }
+    mpasoField->mGrid = mpasoGrid;
+    if (ID2.has_value()) {
+        auto it2 = mpasoAttributeMap.find(ID2.value());
+        if (it2 == mpasoAttributeMap.end()) {
+            std::fprintf(stderr, "[MOPSApp]::activeAttribute: solID %d not found\n", ID2.value());
+            return;
+        }
+        mpasoField->mSol_Front = it->second;
+        mpasoField->mSol_Back = it2->second;
+        mFrontID = ID1; mBackID = ID2.value(); mHasBack = true;
+        residentSlot(mFrontID);
+        residentSlot(mBackID);
+    } else {
+        mpasoField->mSol_Front = it->second;
+        mFrontID = ID1; mHasBack = false;
+        residentSlot(mFrontID);
+    }
+}
+
+int MOPSApp::locate(const std::vector<CartesianCoord>& pts, std::vector<int>& cells)
+{
+    cells.assign(pts.size(), -1);
+    if (pts.empty()) return 0;
+    static_assert(sizeof(int) == sizeof(int32_t), "int32 cells");
+    const int rc = mops_locate(mCtx, MOPS_MEM_HOST, static_cast<int64_t>(pts.size()), reinterpret_cast<const double*>(pts.data()), cells.data());
+    if (rc != MOPS_OK) engine_error(mCtx, "locate", rc);
+    return rc;
+}
+
+namespace {
+// TrajectoryCommon.h:29-41: per-particle depths only when sized like the seeds, else the uniform depth
+std::vector<float> effective_depths(const TrajectorySettings* cfg, size_t n)
+{
+    if (cfg->hasPerParticleDepths() && cfg->particle_depths.size() == n) return cfg->particle_depths;
+    return std::vector<float>(n, cfg->depth);
+}
+
+std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, int slot_b, TrajectorySettings* config,
+                                      std::vector<CartesianCoord>& seeds, const char* what)
+{
+    std::vector<TrajectoryLine> lines;
+    if (config == nullptr || seeds.empty()) return lines; // VK:659-665
+    if (config->deltaT == 0 || config->recordT == 0 || config->simulationDuration == 0) {
+        std::fprintf(stderr, "[B200::%s] invalid trajectory settings\n", what); // VK:666-669
+        return lines;
+    }
+    const size_t n = seeds.size();
+    const size_t each = config->simulationDuration / config->recordT;
+    const size_t times = config->simulationDuration / config->deltaT;
+    std::vector<float> depths = effective_depths(config, n);
+    const std::vector<float> depths0 = depths;
+    if (each == 0 || times == 0) {
+        // VK:709-712 returns the initialised lines: seed only
+        std::fprintf(stderr, "[B200::%s] invalid integration steps\n", what);
+        lines.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            lines[i].lineID = static_cast<int>(i);
+            lines[i].points.push_back(seeds[i]);
+            lines[i].lastPoint = seeds[i];
+            lines[i].duration = static_cast<double>(config->simulationDuration);
+            lines[i].timestamp = static_cast<double>(config->deltaT);
+            lines[i].depth = depths0[i];
+        }
+        return lines;
+    }
+    std::vector<CartesianCoord> pos = seeds; // stable_points
+    std::vector<double> raw_pos(n * each * 3), raw_vel(n * each * 3);
+    mops_traj_cfg cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.method = (config->methodType == CalcMethodType::kEuler) ? MOPS_METHOD_EULER : MOPS_METHOD_RK4;
+    cfg.direction = (config->directionType == CalcDirection::kForward) ? MOPS_DIR_FORWARD : MOPS_DIR_BACKWARD;
+    cfg.delta_t = static_cast<int64_t>(config->deltaT);
+    cfg.duration = static_cast<int64_t>(config->simulationDuration);
+    cfg.record_t = static_cast<int64_t>(config->recordT);
+    cfg.mem = MOPS_MEM_HOST;
+    cfg.sort_particles = 1;
+    mops_traj_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.n = static_cast<int64_t>(n);
+    io.xyz = reinterpret_cast<double*>(pos.data());
+    io.depth = depths.data();
+    io.cell0 = nullptr; // located on the device (replaces MPASOField::calcInWhichCells)
+    io.out_pos = raw_pos.data();
+    io.out_vel = raw_vel.data();
+    mops_traj_stats st;
+    const int rc = path ? mops_pathline(ctx, &cfg, slot_f, slot_b, &io, &st) : mops_streamline(ctx, &cfg, slot_f, &io, &st);
+    if (rc != MOPS_OK) {
+        engine_error(ctx, what, rc);
+        return lines;
+    }
+    book().add(std::string("GPUKernel::") + what + "::kernel", 4, st.kernel_ms);
+    book().add(std::string("MemoryCopy::") + what, 3, st.total_ms - st.kernel_ms - st.locate_ms);
+
+    // line assembly + NaN trimming (TrajectoryCommon.h:43-190) on the flat buffers
+    const size_t per = each + 1;
+    std::vector<double> pts(n * per * 3), vel(n * per * 3), temp(n * per), sal(n * per), last(n * 3);
+    mops_finalize_lines(static_cast<int64_t>(n), static_cast<int32_t>(each), reinterpret_cast<const double*>(seeds.data()), raw_pos.data(),
+                        raw_vel.data(), path ? 1 : 0, pts.data(), vel.data(), temp.data(), sal.data(), last.data());
+    lines.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        TrajectoryLine& ln = lines[i];
+        ln.lineID = static_cast<int>(i);
+        ln.points.resize(per);
+        ln.velocity.resize(per);
+        std::memcpy(ln.points.data(), pts.data() + i * per * 3, per * 24);
+        std::memcpy(ln.velocity.data(), vel.data() + i * per * 3, per * 24);
+        ln.temperature.assign(temp.begin() + i * per, temp.begin() + (i + 1) * per);
+        ln.salinity.assign(sal.begin() + i * per, sal.begin() + (i + 1) * per);
+        ln.lastPoint = CartesianCoord(last[3 * i], last[3 * i + 1], last[3 * i + 2]);
+        ln.duration = static_cast<double>(config->simulationDuration);
+        ln.timestamp = static_cast<double>(config->deltaT);
+        ln.depth = depths0[i];
+    }
+    return lines;
+}
+} // namespace
+
+std::vector<TrajectoryLine> MOPSApp::runStreamLine(TrajectorySettings* config, std::vector<CartesianCoord>& sample_points)
+{
+    Scope sc("GPUKernel::StreamLine", 6); // whole call booked under "Other"; kernel time goes to GPUKernel
+    if (!mpasoField || !mpasoField->mSol_Front) {
+        std::fprintf(stderr, "[MOPSApp]::mpasoField is nullptr, please activeAttribute first\n");
+        return {};
+    }
+    return run_lines(mCtx, false, residentSlot(mFrontID), -1, config, sample_points, "StreamLine");
+}
+
+std::vector<TrajectoryLine> MOPSApp::runPathLine(TrajectorySettings* config, std::vector<CartesianCoord>& sample_points)
+{
+    Scope sc("GPUKernel::PathLine", 6);
+    if (!mpasoField) { // src/Core/MOPSApp.cpp:259-264
+        std::fprintf(stderr, "[MOPSApp]::mpasoField is nullptr, please activeAttribute first\n");
+        std::exit(-1);
+    }
+    if (!mpasoField->mSol_Front || !mpasoField->mSol_Back || !mHasBack) { // :266-271
+        std::fprintf(stderr, "[MOPSApp]::Sol_Front or Sol_Back is nullptr, please activeAttribute first\n");
+        std::exit(-1);
+    }
+    const int sf = residentSlot(mFrontID), sb = residentSlot(mBackID);
+    auto lines = run_lines(mCtx, true, sf, sb, config, sample_points, "PathLine");
+    // the caller's seeds become each line's lastPoint (src/Core/MOPSApp.cpp:287-290, R14)
+    for (size_t i = 0; i < sample_points.size() && i < lines.size(); ++i) sample_points[i] = lines[i].lastPoint;
+    return lines;
+}
+
+std::vector<ImageBuffer<double>> MOPSApp::runRemapping(VisualizationSettings* config)
+{
+    Scope sc("GPUKernel::Remapping", 6);
+    std::vector<ImageBuffer<double>> img_vec;
+    if (!config || !mpasoField || !mpasoField->mSol_Front) {
+        std::fprintf(stderr, "[B200::VisualizeFixedDepth] invalid inputs\n");
+        return img_vec;
+    }
+    const int w = static_cast<int>(config->imageSize.x()), h = static_cast<int>(config->imageSize.y());
+    // image 0 = velocity, then ceil(nAttr/3) attribute images (src/Core/MOPSApp.cpp:176-185)
+    const size_t attr_size = mpasoField->mSol_Front->mDoubleAttributes.size();
+    img_vec.emplace_back(w, h);
+    if (attr_size > 0)
+        for (size_t i = 0; i < (attr_size + 2) / 3; ++i) img_vec.emplace_back(w, h);
+    mops_remap_cfg cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.width = w; cfg.height = h;
+    cfg.lat_min = config->LatRange.x(); cfg.lat_max = config->LatRange.y();
+    cfg.lon_min = config->LonRange.x(); cfg.lon_max = config->LonRange.y();
+    cfg.fixed_depth = config->FixedDepth;
+    cfg.mem = MOPS_MEM_HOST;
+    mops_remap_stats st;
+    const int rc = mops_remap_fixed_depth(mCtx, &cfg, residentSlot(mFrontID), img_vec[0].mPixels.data(),
+                                          img_vec.size() > 1 ? img_vec[1].mPixels.data() : nullptr, nullptr, &st);
+    if (rc != MOPS_OK) engine_error(mCtx, "runRemapping", rc);
+    else {
+        book().add("GPUKernel::Remapping::kernel", 4, st.kernel_ms);
+        book().add("MemoryCopy::Remapping", 3, st.total_ms - st.kernel_ms);
+    }
+    return img_vec;
+}
+
+void MOPSApp::generateSamplePoints(SamplingSettings* config, std::vector<CartesianCoord>& points)
+{
+    // MPASOVisualizer::GenerateSamplePoint (src/Core/MPASOVisualizer.cpp:120-149): floating
+    // accumulation loops, then EVERY point of the vector is converted (lon, lat, depth) -> XYZ at
+    // r = 6371010 regardless of depth (R15)
+    const double minLat = config->getLatitudeRange().x(), maxLat = config->getLatitudeRange().y();
+    const double minLon = config->getLongitudeRange().x(), maxLon = config->getLongitudeRange().y();
+    const double i_step = (maxLat - minLat) / static_cast<double>(config->getSampleRange().x() - 1);
+    const double j_step = (maxLon - minLon) / static_cast<double>(config->getSampleRange().y() - 1);
+    for (double i = minLat; i < maxLat; i += i_step)
+        for (double j = minLon; j < maxLon; j += j_step) points.push_back(CartesianCoord(j, i, config->getDepth()));
+    for (auto& p : points) {
+        const double theta = p.y() * (M_PI / 180.0), phi = p.x() * (M_PI / 180.0);
+        const double r = 6371010.0f;
+        const double costheta = std::cos(theta), cosphi = std::cos(phi), sintheta = std::sin(theta), sinphi = std::sin(phi);
+        p = CartesianCoord(r * costheta * cosphi, r * costheta * sinphi, r * sintheta);
+    }
+}
+
+void MOPSApp::generateSamplePointsAtCenter(SamplingSettings*, std::vector<CartesianCoord>& points)
+{
+    for (auto& c : mpasoGrid->cellCoord_vec) points.push_back(c); // src/Core/MOPSApp.cpp:217-229
+}
+
+bool MOPSApp::checkAttribute() const
+{
+    if (!mpasoGrid) {
+        std::fprintf(stderr, "[MOPSApp]::Grid is nullptr\n");
+        return false;
+    }
+    if (!mpasoGrid->checkAttribute()) {
+        std::fprintf(stderr, "[MOPSApp]::Grid attribute check failed\n");
+        return false;
+    }
+    for (auto& kv : mpasoAttributeMap) {
+        if (!kv.second) {
+            std::fprintf(stderr, "[MOPSApp]::Solution at solID %d is nullptr\n", kv.first);
+            return false;
+        }
+        if (!kv.second->checkAttribute()) {
+            std::fprintf(stderr, "[MOPSApp]::Attribute check failed at solID %d\n", kv.first);
+            return false;
+        }
+    }
+    return true;
+}
+
+// =================================================================================================
+// free functions (src/Core/MOPS.cpp:10-127)
+// =================================================================================================
+void MOPS_Init(const char* device) { app.init(device); }
+void MOPS_Begin() { app.setState(MOPSState::Configuring); }
+void MOPS_AddGridMesh(std::shared_ptr<MPASOGrid> grid) { app.addGrid(std::move(grid)); }
+void MOPS_AddAttribute(int solID, std::shared_ptr<MPASOSolution> sol) { app.addSol(solID, std::move(sol)); }
+void MOPS_End()
+{
+    if (app.getState() != MOPSState::Configuring) {
+        std::cerr << " [ MOPS is not configuring ]\n";
+        std::exit(1);
+    }
+    if (!app.checkAttribute()) {
+        std::cerr << " [ MOPS is not configured ]\n";
+        std::exit(1);
+    }
+    app.setState(MOPSState::Ready);
+    app.addField();
+}
+void MOPS_ActiveAttribute(int t1, std::optional<int> t2) { app.activeAttribute(t1, t2); }
+std::vector<ImageBuffer<double>> MOPS_RunRemapping(VisualizationSettings* config) { return app.runRemapping(config); }
+std::vector<TrajectoryLine> MOPS_RunStreamLine(TrajectorySettings* config, std::vector<CartesianCoord>& pts) { return app.runStreamLine(config, pts); }
+std::vector<TrajectoryLine> MOPS_RunPathLine(TrajectorySettings* config, std::vector<CartesianCoord>& pts) { return app.runPathLine(config, pts); }
+void MOPS_GenerateSamplePoints(SamplingSettings* config, std::vector<CartesianCoord>& pts)
+{
+    if (!config->isAtCellCenter()) app.generateSamplePoints(config, pts);
+    else app.generateSamplePointsAtCenter(config, pts);
+}
+std::shared_ptr<MPASOField> MOPS_GetFieldSnapshots() { return app.getField(); }
+
+void MOPS_ResetTiming()
+{
+    std::lock_guard<std::mutex> g(book().mu);
+    book().entries.clear();
+}
+void MOPS_PrintTimingSummary()
+{
+    std::printf("==== MOPS timing summary (ms) ====\n");
+    double total = 0.0;
+    for (int c = 0; c < 7; ++c) {
+        const double t = book().category(c);
+        total += t;
+        if (t > 0.0) std::printf("  %-14s %12.3f\n", kCategories[c], t);
+    }
+    std::printf("  %-14s %12.3f\n", "Total", total);
+}
+void MOPS_PrintTimingDetailed()
+{
+    std::lock_guard<std::mutex> g(book().mu);
+    std::printf("==== MOPS timing detail (ms) ====\n");
+    for (auto& e : book().entries) std::printf("  [%-13s] %-40s %12.3f\n", kCategories[e.category], e.name.c_str(), e.ms);
+}
+double MOPS_GetCategoryTime(const char* category) { return book().category(category_index(category)); }
+double MOPS_GetTotalTime()
+{
+    double t = 0.0;
+    for (int c = 0; c < 7; ++c) t += book().category(c);
+    return t;
+}
+
+} // namespace MOPS

@@ -258,3 +258,23 @@ def uniform_sphere_seeds(n: int, seed: int, lat_max: float = 80.0, radius: float
     lon = rng.uniform(-np.pi, np.pi, size=n)
     rxy = np.sqrt(1.0 - z * z)
     return np.stack([radius * rxy * np.cos(lon), radius * rxy * np.sin(lon), radius * z], axis=1)
+
+
+def dump_fixture(path: str, mesh: Mesh, snaps) -> None:
+    """Flat binary fixture the C++ tutorials read (tutorial/fixture.hpp): 'MOPSFIX1', six int32
+    sizes, mesh arrays, then per snapshot zonal / meridional / layerThickness / bottomDepth /
+    vertVelocityTop and the named scalar attributes (32-byte name + values)."""
+    names = sorted(snaps[0].attrs.keys())
+    L = snaps[0].n_levels
+    with open(path, "wb") as f:
+        f.write(b"MOPSFIX1")
+        np.array([mesh.n_cells, mesh.n_vertices, mesh.max_edges, L, len(snaps), len(names)], dtype=np.int32).tofile(f)
+        for a, dt in ((mesh.cell_xyz, np.float64), (mesh.vertex_xyz, np.float64), (mesh.vertices_on_cell, np.int32),
+                      (mesh.cells_on_cell, np.int32), (mesh.cells_on_vertex, np.int32), (mesh.n_edges_on_cell, np.int32)):
+            np.ascontiguousarray(a, dtype=dt).tofile(f)
+        for s in snaps:
+            for a in (s.zonal, s.meridional, s.layer_thickness, s.bottom_depth, s.vert_vel_top):
+                np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+            for n in names:
+                f.write(n.encode().ljust(32, b"\0"))
+                np.ascontiguousarray(s.attrs[n], dtype=np.float64).tofile(f)

@@ -1,0 +1,4 @@
+set -x
+nvidia-smi -L
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ) > gpurun_out/bench_n2.log 2>&1
+tail -c 3500 gpurun_out/bench_n2.log
