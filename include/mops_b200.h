@@ -58,6 +58,13 @@ enum { MOPS_MEM_HOST = 0, MOPS_MEM_DEVICE = 1 };
 /* CalcMethodType / CalcDirection of the reference, src/Core/MPASOVisualizer.h:16-17 */
 enum { MOPS_METHOD_RK4 = 0, MOPS_METHOD_EULER = 1 };
 enum { MOPS_DIR_FORWARD = 0, MOPS_DIR_BACKWARD = 1 };
+/* MOPS_SEM_REFERENCE: the reference's semantics, bit for bit -- every RK stage is evaluated in the
+ * start-of-step cell and a stage point outside it stops the particle for good (VK:753-756, 930-957).
+ * MOPS_SEM_WALK: NOT a parity mode -- each stage point is evaluated in the cell that contains it
+ * (cellsOnCell walk to the nearest centre), so particles cross cells under RK4 as they do under
+ * Euler; validated against the analytic solid-body solution, identical to the reference until the
+ * step where the reference would stop the particle. */
+enum { MOPS_SEM_REFERENCE = 0, MOPS_SEM_WALK = 1 };
 
 /* why a particle stopped (the reference's kernels just `return`) */
 enum {
@@ -142,7 +149,12 @@ typedef struct mops_traj_cfg {
     int64_t record_t;       /* seconds         (TrajectorySettings::recordT)                 */
     int32_t mem;            /* MOPS_MEM_*: space of all particle / output pointers           */
     int32_t sort_particles; /* 1: process particles in Morton-cell order (results unchanged) */
-    int32_t reserved[4];
+    int32_t count_near_edge;/* 1: track, per particle, the smallest angular distance [rad] between any
+                               evaluated point and an edge of the cell it was evaluated in; particles
+                               closer than 1e-12 rad are counted in mops_traj_stats (the band in which
+                               a differently-rounded sin/cos may legitimately flip a cell decision) */
+    int32_t semantics;      /* MOPS_SEM_REFERENCE (default) or MOPS_SEM_WALK                        */
+    int32_t reserved[2];
 } mops_traj_cfg;
 
 typedef struct mops_traj_io {
@@ -157,6 +169,7 @@ typedef struct mops_traj_io {
     int32_t* out_status;    /* [n] MOPS_ST_* or NULL                                          */
     int32_t* out_steps;     /* [n] steps started (alive at step start) or NULL                */
     int32_t* out_cell;      /* [n] last cell or NULL                                          */
+    double* out_min_edge;   /* [n] smallest edge distance [rad] seen (count_near_edge) or NULL        */
 } mops_traj_io;
 
 typedef struct mops_traj_stats {
@@ -167,6 +180,7 @@ typedef struct mops_traj_stats {
     double total_ms;        /* whole call on the stream (copies included)                     */
     int32_t launches;       /* kernels of this library launched by the call                   */
     int32_t reserved;
+    int64_t near_edge_particles; /* particles that came within 1e-12 rad of a cell edge (count_near_edge) */
 } mops_traj_stats;
 
 /* replaces MOPS::Factory::StreamLine (src/Common/MOPSFactory.h:28-33 -> VK:653-1015) */

@@ -21,6 +21,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 METHOD_RK4, METHOD_EULER = 0, 1
 DIR_FORWARD, DIR_BACKWARD = 0, 1
 MAX_SLOTS = 4
+SEM_REFERENCE, SEM_WALK = 0, 1
 STATUS_NAMES = {0: "alive", 1: "bad_cell", 2: "not_in_cell", 3: "bad_column", 4: "zero_velocity",
                 5: "above_surface", 6: "bad_setup"}
 
@@ -35,18 +36,20 @@ ABI_SYMBOLS = [
 
 class TrajCfg(C.Structure):
     _fields_ = [("method", C.c_int32), ("direction", C.c_int32), ("delta_t", C.c_int64), ("duration", C.c_int64),
-                ("record_t", C.c_int64), ("mem", C.c_int32), ("sort_particles", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("record_t", C.c_int64), ("mem", C.c_int32), ("sort_particles", C.c_int32), ("count_near_edge", C.c_int32),
+                ("semantics", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class TrajIO(C.Structure):
     _fields_ = [("n", C.c_int64), ("xyz", C.c_void_p), ("depth", C.c_void_p), ("cell0", C.c_void_p),
                 ("out_pos", C.c_void_p), ("out_vel", C.c_void_p), ("out_attr", C.c_void_p), ("out_cell_log", C.c_void_p),
-                ("out_status", C.c_void_p), ("out_steps", C.c_void_p), ("out_cell", C.c_void_p)]
+                ("out_status", C.c_void_p), ("out_steps", C.c_void_p), ("out_cell", C.c_void_p), ("out_min_edge", C.c_void_p)]
 
 
 class TrajStats(C.Structure):
     _fields_ = [("particle_steps", C.c_int64), ("alive_at_end", C.c_int64), ("kernel_ms", C.c_double),
-                ("locate_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("locate_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_int32), ("reserved", C.c_int32),
+                ("near_edge_particles", C.c_int64)]
 
 
 class RemapCfg(C.Structure):
@@ -233,7 +236,7 @@ class Engine:
 
     # ---- trajectories ----------------------------------------------------------------------
     def _traj(self, path, slots, seeds, delta_t, duration, record_t, depth, depths, cell0, method, direction,
-              log_cells, sort_particles, want_attr):
+              log_cells, sort_particles, want_attr, near_edge=False, walk=False):
         seeds = np.array(seeds, dtype=np.float64, order="C", copy=True)
         n = seeds.shape[0]
         each = int(duration) // int(record_t) if record_t else 0
@@ -244,10 +247,12 @@ class Engine:
         log = np.zeros((n, max(times, 0)), dtype=np.int32) if log_cells else None
         status = np.zeros(n, dtype=np.int32); steps = np.zeros(n, dtype=np.int32); fcell = np.zeros(n, dtype=np.int32)
         c0 = _np(cell0, np.int32)
+        edge = np.zeros(n) if near_edge else None
         cfg = TrajCfg(METHOD_RK4 if method == "rk4" else METHOD_EULER, DIR_FORWARD if direction == "forward" else DIR_BACKWARD,
-                      int(delta_t), int(duration), int(record_t), MEM_HOST, 1 if sort_particles else 0)
+                      int(delta_t), int(duration), int(record_t), MEM_HOST, 1 if sort_particles else 0,
+                      1 if near_edge else 0, SEM_WALK if walk else SEM_REFERENCE)
         io = TrajIO(n, _ptr(seeds), _ptr(dep), _ptr(c0), _ptr(out_pos), _ptr(out_vel), _ptr(out_attr), _ptr(log),
-                    _ptr(status), _ptr(steps), _ptr(fcell))
+                    _ptr(status), _ptr(steps), _ptr(fcell), _ptr(edge))
         st = TrajStats()
         if path:
             rc = self.lib.mops_pathline(self.h, C.byref(cfg), slots[0], slots[1], C.byref(io), C.byref(st))
@@ -255,17 +260,17 @@ class Engine:
             rc = self.lib.mops_streamline(self.h, C.byref(cfg), slots[0], C.byref(io), C.byref(st))
         self._ck(rc)
         return {"raw_pos": out_pos, "raw_vel": out_vel, "raw_attr": out_attr, "pos": seeds, "depth": dep, "cell_log": log,
-                "status": status, "steps_alive": steps, "final_cell": fcell, "stats": st}
+                "status": status, "steps_alive": steps, "final_cell": fcell, "min_edge": edge, "stats": st}
 
     def streamline(self, slot, seeds, delta_t, duration, record_t, depth=0.0, depths=None, cell0=None, method="rk4",
-                   direction="forward", log_cells=False, sort_particles=True):
+                   direction="forward", log_cells=False, sort_particles=True, near_edge=False, walk=False):
         return self._traj(False, (slot, slot), seeds, delta_t, duration, record_t, depth, depths, cell0, method, direction,
-                          log_cells, sort_particles, False)
+                          log_cells, sort_particles, False, near_edge, walk)
 
     def pathline(self, front, back, seeds, delta_t, duration, record_t, depth=0.0, depths=None, cell0=None, method="rk4",
-                 direction="forward", log_cells=False, sort_particles=True, want_attr=True):
+                 direction="forward", log_cells=False, sort_particles=True, want_attr=True, near_edge=False, walk=False):
         return self._traj(True, (front, back), seeds, delta_t, duration, record_t, depth, depths, cell0, method, direction,
-                          log_cells, sort_particles, want_attr)
+                          log_cells, sort_particles, want_attr, near_edge, walk)
 
     def traj_device(self, path, slots, cfg: TrajCfg, io: TrajIO, want_stats=True) -> Optional[TrajStats]:
         """device-resident call: the caller filled io with torch data_ptr()s and cfg.mem = MEM_DEVICE"""

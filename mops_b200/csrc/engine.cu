@@ -71,7 +71,7 @@ struct mops_ctx {
     Buf st_zonal, st_merid, st_thick, st_wtop, st_bottom, st_ztopc, st_attr, st_vmono;
     int* d_nonmono = nullptr;
     // particle scratch (host-memory mode) + sort scratch
-    Buf p_xyz, p_depth, p_cell0, p_cell_int, p_out_pos, p_out_vel, p_out_attr, p_log, p_status, p_steps, p_fcell;
+    Buf p_xyz, p_depth, p_cell0, p_cell_int, p_out_pos, p_out_vel, p_out_attr, p_log, p_status, p_steps, p_fcell, p_edge;
     Buf s_keys, s_vals, s_keys2, s_vals2, s_tmp;
     Buf r_img0, r_img1, r_cells;
     unsigned long long* counters = nullptr; // [4]
@@ -457,6 +457,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     double *d_xyz, *d_out_pos, *d_out_vel, *d_out_attr = nullptr;
     float* d_depth;
     int *d_log = nullptr, *d_status = nullptr, *d_steps = nullptr, *d_fcell = nullptr;
+    double* d_edge = nullptr;
     const int* d_cell0_ext = nullptr;
     if (host) {
         if ((rc = ensure(ctx, ctx->p_xyz, (size_t)n * 24))) return rc;
@@ -477,10 +478,12 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
         if (io->out_status) { if ((rc = ensure(ctx, ctx->p_status, (size_t)n * 4))) return rc; d_status = (int*)ctx->p_status.p; }
         if (io->out_steps) { if ((rc = ensure(ctx, ctx->p_steps, (size_t)n * 4))) return rc; d_steps = (int*)ctx->p_steps.p; }
         if (io->out_cell) { if ((rc = ensure(ctx, ctx->p_fcell, (size_t)n * 4))) return rc; d_fcell = (int*)ctx->p_fcell.p; }
+        if (io->out_min_edge) { if ((rc = ensure(ctx, ctx->p_edge, (size_t)n * 8))) return rc; d_edge = (double*)ctx->p_edge.p; }
     } else {
         d_xyz = io->xyz; d_depth = io->depth; d_out_pos = io->out_pos; d_out_vel = io->out_vel;
         d_out_attr = want_attr ? io->out_attr : nullptr;
         d_log = io->out_cell_log; d_status = io->out_status; d_steps = io->out_steps; d_fcell = io->out_cell;
+        d_edge = io->out_min_edge;
         d_cell0_ext = io->cell0;
     }
     // the reference's output buffers are value-initialised (TrajectoryCommon.h:20-25)
@@ -537,6 +540,9 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     P.pos = d_xyz; P.depth = d_depth; P.cell0 = d_cell_int;
     P.out_pos = d_out_pos; P.out_vel = d_out_vel; P.out_attr = d_out_attr;
     P.cell_log = d_log; P.status = d_status; P.steps = d_steps; P.fcell = d_fcell;
+    P.min_edge = d_edge;
+    P.diag_edge = (cfg->count_near_edge || d_edge) ? 1 : 0;
+    P.walk = (cfg->semantics == MOPS_SEM_WALK) ? 1 : 0;
     P.counters = ctx->counters;
 
     CK(cudaEventRecord(ctx->ev1, st));
@@ -561,6 +567,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
         if (d_status) CK(cudaMemcpyAsync(io->out_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (d_steps) CK(cudaMemcpyAsync(io->out_steps, d_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (d_fcell) CK(cudaMemcpyAsync(io->out_cell, d_fcell, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (d_edge) CK(cudaMemcpyAsync(io->out_min_edge, d_edge, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     }
     // host-memory calls complete before returning; device-memory calls stay asynchronous on the
     // context's stream unless the caller asks for stats
@@ -573,6 +580,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
         std::memset(stats, 0, sizeof(*stats));
         stats->particle_steps = (int64_t)h_counters[0];
         stats->alive_at_end = (int64_t)h_counters[1];
+        stats->near_edge_particles = (int64_t)h_counters[3];
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev_kend) == cudaSuccess) stats->kernel_ms = ms;
         if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) stats->locate_ms = ms;
@@ -651,7 +659,7 @@ void mops_destroy(mops_ctx* ctx)
     }
     Buf* bufs[] = {&ctx->st_zonal, &ctx->st_merid, &ctx->st_thick, &ctx->st_wtop, &ctx->st_bottom, &ctx->st_ztopc, &ctx->st_attr,
                    &ctx->st_vmono, &ctx->p_xyz, &ctx->p_depth, &ctx->p_cell0, &ctx->p_cell_int, &ctx->p_out_pos, &ctx->p_out_vel,
-                   &ctx->p_out_attr, &ctx->p_log, &ctx->p_status, &ctx->p_steps, &ctx->p_fcell, &ctx->s_keys, &ctx->s_vals,
+                   &ctx->p_out_attr, &ctx->p_log, &ctx->p_status, &ctx->p_steps, &ctx->p_fcell, &ctx->p_edge, &ctx->s_keys, &ctx->s_vals,
                    &ctx->s_keys2, &ctx->s_vals2, &ctx->s_tmp, &ctx->r_img0, &ctx->r_img1, &ctx->r_cells};
     for (Buf* b : bufs) cudaFree(b->p);
     cudaFree(ctx->counters);

@@ -63,6 +63,21 @@ enum {
 // returns false when the point is not in the cell (IsInMesh).  w[] are the normalised
 // weights, vo[i] = vid[i]*L (row offsets into the vertex-major arrays); wfinite tells
 // whether all weights are finite (a point exactly on an edge gives inf/NaN, Appendix B N7).
+// Diagnostic only (cfg.count_near_edge): smallest angular distance of p to the great circles through
+// the cell's edges, |dot(n_k, p)| / (|n_k| |p|) ~ angle for small angles.
+template <int M>
+__device__ __noinline__ double min_edge_angle(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz)
+{
+    double best = 1.0e300;
+    const double pl = len3(px, py, pz);
+    for (int k = 0; k < nv; ++k) {
+        const double direction = rec->nx[k] * px + rec->ny[k] * py + rec->nz[k] * pz;
+        const double a = fabs(direction) / (len3(rec->nx[k], rec->ny[k], rec->nz[k]) * pl);
+        if (a < best) best = a;
+    }
+    return best;
+}
+
 template <int M>
 __device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
                                              double (&w)[M], bool& wfinite)

@@ -338,7 +338,10 @@ struct AdvectParams {
     int* status;      // or null
     int* steps;       // or null
     int* fcell;       // or null (caller cell ids)
-    unsigned long long* counters; // [0] particle-steps started, [1] alive at end
+    double* min_edge; // or null: per-particle smallest edge distance [rad] (diagnostic)
+    int diag_edge;    // 1 = track the smallest edge distance of every evaluated point
+    int walk;         // 1 = MOPS_SEM_WALK: evaluate each stage point in the cell that contains it
+    unsigned long long* counters; // [0] particle-steps started, [1] alive at end, [3] near-edge particles
 };
 
 __device__ __forceinline__ void st3(double* p, long long i, double x, double y, double z)
@@ -352,7 +355,7 @@ template <int M, bool PATH, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
 {
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long my_steps = 0, my_alive = 0;
+    unsigned long long my_steps = 0, my_alive = 0, my_near = 0;
     if (tix < P.n) {
         const long long pid = P.order ? (long long)P.order[tix] : tix;
         const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
@@ -368,6 +371,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
         int upd = 0;
         int hint_f = -1, hint_b = -1;
         bool first_vel = true;
+        double edge_min = 1.0e300;
 
         if (cell < 0 || cell >= P.nC) {
             status = ST_BAD_CELL; // VK:895-897: nothing is written, not even the seed
@@ -399,6 +403,8 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                         if (len < min_len) { min_len = len; best = cell; }
                     }
                     if (best != cell) { cell = best; }
+                    // walk mode: not limited to one ring (identical whenever the step is shorter than a cell)
+                    if (P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
                 }
                 ++started;
                 if (P.cell_log) P.cell_log[pid * (long long)P.times + step] = P.c_int2ext[cell];
@@ -427,8 +433,20 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                         p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5);
                         if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
                     }
-                    st = PATH ? eval_path<M>(rec, P.sv, mono_f, mono_b, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
-                              : eval_stream<M>(rec, P.sv[0], mono_f, P.L, p, cur_depth, hint_f, o);
+                    const CellRec<M>* __restrict__ rec_s = rec;
+                    bool mf = mono_f, mb = mono_b;
+                    if (P.walk && s > 0) { // MOPS_SEM_WALK: the cell that contains this stage point
+                        const int cs = walk_nearest<M>(recs, P.c4, cell, p.x, p.y, p.z);
+                        rec_s = recs + cs;
+                        mf = P.sv[0].mono[cs] != 0;
+                        mb = PATH ? (P.sv[1].mono[cs] != 0) : false;
+                    }
+                    if (P.diag_edge) {
+                        const double a = min_edge_angle<M>(rec_s, rec_s->nv, p.x, p.y, p.z);
+                        if (a < edge_min) edge_min = a;
+                    }
+                    st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                              : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
                     if (st != ST_ALIVE) break;
                     if (s == 0) {
                         hvel = mk3(o.hx, o.hy, o.hz);
@@ -492,18 +510,22 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
         if (P.status) P.status[pid] = status;
         if (P.steps) P.steps[pid] = started;
         if (P.fcell) P.fcell[pid] = (cell >= 0 && cell < P.nC) ? P.c_int2ext[cell] : -1;
+        if (P.min_edge) P.min_edge[pid] = edge_min;
         my_steps = (unsigned long long)started;
         my_alive = (status == ST_ALIVE) ? 1ull : 0ull;
+        my_near = (P.diag_edge && edge_min < 1e-12) ? 1ull : 0ull;
     }
     // one atomic pair per warp
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
         my_alive += __shfl_xor_sync(0xffffffffu, my_alive, off);
+        my_near += __shfl_xor_sync(0xffffffffu, my_near, off);
     }
     if ((threadIdx.x & 31) == 0 && P.counters) {
         atomicAdd(P.counters + 0, my_steps);
         atomicAdd(P.counters + 1, my_alive);
+        if (my_near) atomicAdd(P.counters + 3, my_near);
     }
 }
 
