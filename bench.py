@@ -5,7 +5,7 @@ Workload (config C5 of BASELINE.json): pathline, 64 M seeds (stron
 64 M / N per GPU), synthetic icosahedral-Voronoi MPAS mesh with 2,621,442 cells x 80 layers,
 solid-body-rotation snapshots, RK4, dt = 120 s, depth 800 m.  One bench "step" = one
 MOPS_RunPathLine-equivalent call (mops_pathline through the C ABI) over one snapshot interval
-of `--interval-steps` RK4 steps (default 30 of the 720 a 1-day interval has, so that the
+of `--interval-steps` RK4 steps (default 120 of the 720 a 1-day interval has, so that the
 default run ends within minutes; throughput is per particle-step), chained the way the
 reference's tutorial chains intervals (end points -> next seeds, re-located), while the NEXT
 snapshot is uploaded + preprocessed on the side stream from pinned host memory
@@ -145,12 +145,12 @@ def run_cpu_reference(level, L, n_particles, interval_steps, threads=None, targe
         o.activate(0, 1)
         # probe to size the sample for ~target_seconds
         probe_n = min(n_particles, 20000)
-        r = o.pathline(seeds_all[:probe_n], DT, duration, duration, depth=DEPTH)
+        r = o.pathline(seeds_all[:probe_n], DT, duration, min(3600, duration), depth=DEPTH)
         rate = probe_n * interval_steps / max(r["seconds"], 1e-6)
         n = int(min(n_particles, max(probe_n, rate * target_seconds / interval_steps)))
         times = []
         for _ in range(repeats):
-            r = o.pathline(seeds_all[:n], DT, duration, duration, depth=DEPTH)
+            r = o.pathline(seeds_all[:n], DT, duration, min(3600, duration), depth=DEPTH)
             times.append(r["seconds"])
         o.close()
         kind = "reference"
@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--level", type=int, default=9, help="icosahedral bisection level (9 = 2,621,442 cells)")
     ap.add_argument("--layers", type=int, default=80)
     ap.add_argument("--particles", type=int, default=64_000_000, help="TOTAL seeds over all GPUs (strong scaling)")
-    ap.add_argument("--interval-steps", type=int, default=30, help="RK4 steps per snapshot interval (720 = 1 day)")
+    ap.add_argument("--interval-steps", type=int, default=120, help="RK4 steps per snapshot interval (720 = 1 day)")
     ap.add_argument("--cpu-level", type=int, default=7)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -244,12 +244,21 @@ def main():
     def pinned(shape):
         return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
 
-    # two distinct host snapshots (pinned); snapshot s of the chain re-uses ring[s % 2]
+    # distinct host snapshots (pinned); snapshot s of the chain re-uses ring[s % len(ring)].  Two when host
+    # memory allows (all ranks of the box pin theirs at once), else one.
+    snap_host_bytes = 3 * mesh.n_cells * L * 8
+    ring_n = 2
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        if world * (2 * snap_host_bytes + 8e9) > 0.6 * avail:
+            ring_n = 1
+    except Exception:
+        pass
     ring = [make_snapshot_host(mesh, L, 0.02 * (1 + 0.5 * math.sin(2 * math.pi * s / 30)), 0.3 + 0.01 * s, pinned)
-            for s in range(2)]
+            for s in range(ring_n)]
 
     def upload(slot, s, async_):
-        h = ring[s % 2]
+        h = ring[s % ring_n]
         eng.set_snapshot_raw(slot, L, h["zonal"].ctypes.data, h["merid"].ctypes.data, h["thick"].ctypes.data,
                              h["bottom"].ctypes.data, None, async_=async_)
 
@@ -263,9 +272,9 @@ def main():
     seeds_np, _global_idx = sharding.shard_seeds(seeds_all, rank, world)
     del seeds_all
     n = seeds_np.shape[0]
-    each = 2
     duration = DT * args.interval_steps
-    record_t = duration // each
+    record_t = min(3600, duration)  # hourly records
+    each = duration // record_t
 
     xyz = torch.from_numpy(seeds_np).to(dev)
     depth = torch.full((n,), DEPTH, dtype=torch.float32, device=dev)

@@ -380,8 +380,8 @@ template <int M, int MINB>
 void launch_advect_occ(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
     const int grid = blocks_for(P.n, 128);
-    if (path) k_advect<M, true, MINB><<<grid, 128, 0, ctx->stream>>>(P);
-    else k_advect<M, false, MINB><<<grid, 128, 0, ctx->stream>>>(P);
+    if (path) k_advect<M, true, MINB, false><<<grid, 128, 0, ctx->stream>>>(P);
+    else k_advect<M, false, MINB, false><<<grid, 128, 0, ctx->stream>>>(P);
     ctx->launches++;
 }
 
@@ -393,7 +393,7 @@ int advect_minb()
     if (v < 0) {
         const char* e = getenv("MOPS_ADVECT_MINB");
         v = e ? atoi(e) : 3;
-        if (v < 3 || v > 6) v = 3;
+        if (v < 2 || v > 6) v = 3;
     }
     return v;
 }
@@ -401,8 +401,16 @@ int advect_minb()
 template <int M>
 void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
+    if (P.walk || P.diag_edge) { // walk semantics / near-edge diagnostic: the EXTRA instantiation
+        const int grid = blocks_for(P.n, 128);
+        if (path) k_advect<M, true, (M == 20 ? 1 : 3), true><<<grid, 128, 0, ctx->stream>>>(P);
+        else k_advect<M, false, (M == 20 ? 1 : 3), true><<<grid, 128, 0, ctx->stream>>>(P);
+        ctx->launches++;
+        return;
+    }
     if constexpr (M == 6) {
         switch (advect_minb()) {
+        case 2: launch_advect_occ<M, 2>(ctx, P, path); return;
         case 4: launch_advect_occ<M, 4>(ctx, P, path); return;
         case 5: launch_advect_occ<M, 5>(ctx, P, path); return;
         case 6: launch_advect_occ<M, 6>(ctx, P, path); return;

@@ -351,7 +351,10 @@ __device__ __forceinline__ void st3(double* p, long long i, double x, double y, 
 
 __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : ((1.0 < v) ? 1.0 : v); }
 
-template <int M, bool PATH, int MINB>
+// EXTRA = false is the production instantiation; EXTRA = true additionally honours P.walk
+// (MOPS_SEM_WALK) and P.diag_edge (near-edge counting) -- kept out of the hot variant because even
+// never-taken branches cost registers and ~4 % of the kernel time here.
+template <int M, bool PATH, int MINB, bool EXTRA>
 __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
 {
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     }
                     if (best != cell) { cell = best; }
                     // walk mode: not limited to one ring (identical whenever the step is shorter than a cell)
-                    if (P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
+                    if (EXTRA && P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
                 }
                 ++started;
                 if (P.cell_log) P.cell_log[pid * (long long)P.times + step] = P.c_int2ext[cell];
@@ -435,13 +438,13 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     }
                     const CellRec<M>* __restrict__ rec_s = rec;
                     bool mf = mono_f, mb = mono_b;
-                    if (P.walk && s > 0) { // MOPS_SEM_WALK: the cell that contains this stage point
+                    if (EXTRA && P.walk && s > 0) { // MOPS_SEM_WALK: the cell that contains this stage point
                         const int cs = walk_nearest<M>(recs, P.c4, cell, p.x, p.y, p.z);
                         rec_s = recs + cs;
                         mf = P.sv[0].mono[cs] != 0;
                         mb = PATH ? (P.sv[1].mono[cs] != 0) : false;
                     }
-                    if (P.diag_edge) {
+                    if (EXTRA && P.diag_edge) {
                         const double a = min_edge_angle<M>(rec_s, rec_s->nv, p.x, p.y, p.z);
                         if (a < edge_min) edge_min = a;
                     }
@@ -510,10 +513,10 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
         if (P.status) P.status[pid] = status;
         if (P.steps) P.steps[pid] = started;
         if (P.fcell) P.fcell[pid] = (cell >= 0 && cell < P.nC) ? P.c_int2ext[cell] : -1;
-        if (P.min_edge) P.min_edge[pid] = edge_min;
+        if (EXTRA && P.min_edge) P.min_edge[pid] = edge_min;
         my_steps = (unsigned long long)started;
         my_alive = (status == ST_ALIVE) ? 1ull : 0ull;
-        my_near = (P.diag_edge && edge_min < 1e-12) ? 1ull : 0ull;
+        my_near = (EXTRA && P.diag_edge && edge_min < 1e-12) ? 1ull : 0ull;
     }
     // one atomic pair per warp
 #pragma unroll

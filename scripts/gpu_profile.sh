@@ -1,8 +1,9 @@
 set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+( time python bench.py ) > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log | cut -c1-300
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
-tail -3 gpurun_out/plain.log | cut -c1-400
 ncu --set full --clock-control none --import-source on -k regex:k_advect -s 3 -c 1 -f -o gpurun_out/prof_advect $CMD > gpurun_out/ncu_full.log 2>&1
-tail -5 gpurun_out/ncu_full.log
+tail -3 gpurun_out/ncu_full.log | cut -c1-200
 ls -la gpurun_out/
