@@ -11,8 +11,8 @@
 // src/Core/MPASOSolution.cpp:1150-1210; the route pyMOPS uses).  Everything underneath is
 // new: no SYCL/HIP/TBB backends, no dispatch factories, no KD-tree, no disk cache, no CPU path.
 //
-// Out of scope here (SURVEY.md 8, rows marked out of scope / next): file readers
-// (MPASOReader), VTK writers, fixed-layer / fixed-latitude views, the RBF velocity path.
+// Out of scope here (SURVEY.md 8, rows marked out of scope / next): VTK writers, fixed-layer /
+// fixed-latitude views, the RBF velocity path, netCDF-4/HDF5 files (NetCDF-3 only).
 #pragma once
 
 #include <cstddef>
@@ -78,6 +78,28 @@ enum class GridAttributeType : int {
 enum class AttributeFormat : int { kDouble, kFloat, kChar, kVec3, kCount };
 enum class AttributeType : int { kZonalVelocity, kMeridionalVelocity, kVelocity, kNormalVelocity, kZTop, kLayerThickness, kBottomDepth, kCount };
 
+// ---- file ingestion (src/IO/MPASOReader.h; implemented over mops_b200/host/mpas_io.*: YAML-subset
+//      stream description + NetCDF-3 reader, no ndarray / netcdf-c / yaml-cpp) ---------------------
+class MPASOReader {
+public:
+    using Ptr = std::shared_ptr<MPASOReader>;
+    // mesh substream of the YAML stream description (src/IO/MPASOReader.cpp:128-169)
+    static Ptr readGridData(const std::string& yaml_path);
+    // snapshot `timestep` of the data file whose name contains `data_name` (src/IO/MPASOReader.cpp:171-245)
+    static Ptr readSolData(const std::string& yaml_path, const std::string& data_name, const int& timestep);
+
+    std::string path, mMeshName, mDataName, mFolderName, mTimeStamp;
+    int mCellsSize = 0, mEdgesSize = 0, mMaxEdgesSize = 0, mVertexSize = 0, mTimesteps = 0, mVertLevels = 0, mVertLevelsP1 = 0;
+    std::vector<vec3> vertexCoord_vec, cellCoord_vec, edgeCoord_vec;
+    std::vector<vec2> vertexLatLon_vec;
+    std::vector<size_t> verticesOnCell_vec, verticesOnEdge_vec, cellsOnVertex_vec, cellsOnCell_vec, numberVertexOnCell_vec,
+        cellsOnEdge_vec, edgesOnCell_vec;
+    std::vector<double> cellRefBottomDepth_vec;
+    std::vector<double> cellBottomDepth_vec, cellSurfaceHeight_vec, cellZonalVelocity_vec, cellMeridionalVelocity_vec,
+        cellLayerThickness_vec, cellZTop_vec, cellNormalVelocity_vec, cellVertVelocity_vec;
+    std::shared_ptr<void> mGroupT; // the open record (lets MPASOSolution::addAttribute read further variables)
+};
+
 class MPASOGrid {
 public:
     int mCellsSize = 0, mEdgesSize = 0, mMaxEdgesSize = 0, mVertexSize = 0, mTimesteps = 0, mVertLevels = 0, mVertLevelsP1 = 0;
@@ -90,6 +112,7 @@ public:
     std::vector<float> cellWeight_vec;
     std::vector<double> cellRefBottomDepth_vec;
 
+    void initGrid(MPASOReader* reader); // src/Core/MPASOGrid.cpp:190-217 (moves the arrays out of the reader)
     void setGridAttribute(GridAttributeType type, int val);
     void setGridAttributesVec3(GridAttributeType type, const std::vector<vec3>& vec);
     void setGridAttributesVec2(GridAttributeType type, const std::vector<vec2>& vec);
@@ -107,7 +130,12 @@ public:
     std::vector<double> cellLayerThickness_vec, cellZTop_vec, cellVertVelocity_vec, cellNormalVelocity_vec,
         cellMeridionalVelocity_vec, cellZonalVelocity_vec, cellBottomDepth_vec, cellSurfaceHeight_vec;
     std::map<std::string, std::vector<double>> mDoubleAttributes; // e.g. "temperature", "salinity"
+    std::shared_ptr<void> gt; // open record handed over by the reader
 
+    void initSolution(MPASOReader* reader); // src/Core/MPASOSolution.cpp:278-320
+    // read one more cell-major variable of the open record into mDoubleAttributes[name]
+    // (src/Core/MPASOSolution.cpp:381-411); float variables are widened to double
+    void addAttribute(std::string name, AttributeFormat type);
     void setAttribute(GridAttributeType type, int val);
     void setAttributesDouble(AttributeType type, const std::vector<double>& vec);
     void setTimestep(int timestep) { mTimesteps = timestep; }

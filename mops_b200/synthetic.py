@@ -278,3 +278,86 @@ def dump_fixture(path: str, mesh: Mesh, snaps) -> None:
             for n in names:
                 f.write(n.encode().ljust(32, b"\0"))
                 np.ascontiguousarray(s.attrs[n], dtype=np.float64).tofile(f)
+
+
+def write_mpas_files(directory: str, mesh: Mesh, snaps, dates=None, per_file: int = 1, version: int = 2,
+                     alias_names: bool = True) -> str:
+    """Write the fixture as MPAS-Ocean style NetCDF-3 files + the YAML stream description the reference's
+    reader takes (schema of mpas.yaml / tutorial/test.yaml): `<dir>/mesh.nc`, `<dir>/hist.<date>.nc`
+    (Time unlimited, `per_file` snapshots each) and `<dir>/stream.yaml`; returns the YAML path.
+    alias_names writes the time-varying variables under their `timeMonthly_avg_*` names so that the
+    `possible_names` resolution is exercised; tracers are written as float32 (widened on read)."""
+    import os
+    from scipy.io import netcdf_file
+    os.makedirs(directory, exist_ok=True)
+    L = snaps[0].n_levels
+    lat = np.arcsin(mesh.vertex_xyz[:, 2] / np.linalg.norm(mesh.vertex_xyz, axis=1))
+    lon = np.arctan2(mesh.vertex_xyz[:, 1], mesh.vertex_xyz[:, 0])
+    f = netcdf_file(os.path.join(directory, "mesh.nc"), "w", version=version)
+    f.createDimension("nCells", mesh.n_cells)
+    f.createDimension("nVertices", mesh.n_vertices)
+    f.createDimension("maxEdges", mesh.max_edges)
+    f.createDimension("vertexDegree", 3)
+    f.createDimension("nVertLevels", L)
+    for i, n in enumerate("xyz"):
+        f.createVariable(f"{n}Cell", "d", ("nCells",))[:] = mesh.cell_xyz[:, i]
+        f.createVariable(f"{n}Vertex", "d", ("nVertices",))[:] = mesh.vertex_xyz[:, i]
+    f.createVariable("latVertex", "d", ("nVertices",))[:] = lat
+    f.createVariable("lonVertex", "d", ("nVertices",))[:] = lon
+    f.createVariable("verticesOnCell", "i", ("nCells", "maxEdges"))[:] = mesh.vertices_on_cell
+    f.createVariable("cellsOnCell", "i", ("nCells", "maxEdges"))[:] = mesh.cells_on_cell
+    f.createVariable("cellsOnVertex", "i", ("nVertices", "vertexDegree"))[:] = mesh.cells_on_vertex
+    f.createVariable("nEdgesOnCell", "i", ("nCells",))[:] = mesh.n_edges_on_cell
+    f.createVariable("refBottomDepth", "d", ("nVertLevels",))[:] = np.cumsum(np.full(L, 5000.0 / L))
+    f.close()
+
+    pre = "timeMonthly_avg_" if alias_names else ""
+    dates = dates or [f"0001-{1 + i:02d}-01" for i in range((len(snaps) + per_file - 1) // per_file)]
+    names = sorted(snaps[0].attrs.keys())
+    for fi, date in enumerate(dates):
+        chunk = snaps[fi * per_file:(fi + 1) * per_file]
+        f = netcdf_file(os.path.join(directory, f"hist.{date}.nc"), "w", version=version)
+        f.createDimension("Time", None)
+        f.createDimension("nCells", mesh.n_cells)
+        f.createDimension("nVertLevels", L)
+        f.createDimension("nVertLevelsP1", L + 1)
+        f.createDimension("StrLen", 64)
+        xt = f.createVariable("xtime", "c", ("Time", "StrLen"))
+        vz = f.createVariable(pre + "velocityZonal", "d", ("Time", "nCells", "nVertLevels"))
+        vm = f.createVariable(pre + "velocityMeridional", "d", ("Time", "nCells", "nVertLevels"))
+        lt = f.createVariable(pre + "layerThickness", "d", ("Time", "nCells", "nVertLevels"))
+        wv = f.createVariable(pre + "vertVelocityTop", "d", ("Time", "nCells", "nVertLevelsP1"))
+        f.createVariable("bottomDepth", "d", ("nCells",))[:] = chunk[0].bottom_depth
+        tr = {n: f.createVariable(n, "f", ("Time", "nCells", "nVertLevels")) for n in names}
+        for t, s in enumerate(chunk):
+            stamp = f"{date}_{t:02d}:00:00".ljust(64)
+            xt[t] = np.frombuffer(stamp.encode(), dtype="S1")
+            vz[t] = s.zonal; vm[t] = s.meridional; lt[t] = s.layer_thickness; wv[t] = s.vert_vel_top
+            for n in names:
+                tr[n][t] = s.attrs[n].astype(np.float32)
+        f.close()
+
+    def var(name, aliases=None, optional=False):
+        out = f"        - name: {name}\n"
+        if aliases:
+            out += "          possible_names:\n" + "".join(f"            - {a}\n" for a in aliases)
+        if optional:
+            out += "          optional: true\n"
+        return out
+
+    yaml = ("stream:\n  name: mpas\n  path_prefix: \"%s\"\n  substreams:\n"
+            "    - name: mesh\n      format: netcdf\n      filenames: \"mesh.nc\"\n      static: true\n      vars:\n" % directory)
+    for n in ("xCell", "yCell", "zCell", "xVertex", "yVertex", "zVertex", "latVertex", "lonVertex", "nEdgesOnCell", "cellsOnCell",
+              "cellsOnVertex", "verticesOnCell", "refBottomDepth"):
+        yaml += var(n)
+    yaml += "    - name: data\n      format: netcdf\n      filenames: \"hist.*.nc\"   # glob, sorted\n      vars:\n"
+    yaml += var("xtime", ["xtime", "xtime_startMonthly"])
+    for n in ("velocityMeridional", "velocityZonal", "vertVelocityTop", "layerThickness"):
+        yaml += var(n, [n, "timeMonthly_avg_" + n, "timeDaily_avg_" + n], optional=(n == "layerThickness"))
+    yaml += var("bottomDepth")
+    for n in names:
+        yaml += var(n, [n, "timeMonthly_avg_activeTracers_" + n], optional=True)
+    path = os.path.join(directory, "stream.yaml")
+    with open(path, "w") as fh:
+        fh.write(yaml)
+    return path

@@ -66,6 +66,24 @@ def test_streamline_tutorial_config_c1(built, tmp_path):
         assert _vel_close(vel, r["velocity"])
 
 
+def test_streamline_tutorial_from_mpas_files(built, tmp_path):
+    """same run fed from NetCDF-3 files + YAML through MPASOReader: identical lines"""
+    m = cases.mesh(5)
+    s0 = S.solid_body_snapshot(m, 20, 0.5, tilt=0.3, shear=0.2, w_amp=1e-3, with_attrs=True)
+    # float32 tracers in the file: feed the same rounded values through the fixture route
+    s0.attrs = {k: v.astype(np.float32).astype(np.float64) for k, v in s0.attrs.items()}
+    fx = str(tmp_path / "f.bin")
+    S.dump_fixture(fx, m, [s0])
+    yaml = S.write_mpas_files(str(tmp_path / "nc"), m, [s0])
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    subprocess.check_call([os.path.join(built, "streamLine"), fx, a])
+    subprocess.check_call([os.path.join(built, "streamLine"), yaml, b, "0001-01-01"])
+    pa, va, la = _read_lines(a)
+    pb, vb, lb = _read_lines(b)
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(la, lb)
+    assert (pa[:, -1] != 0).any()
+
+
 def test_pathline_tutorial_chained(built, tmp_path):
     from oracle import port_oracle as P
     m = cases.mesh(5)

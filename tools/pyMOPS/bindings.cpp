@@ -8,7 +8,7 @@
 // MOPS_RunRemapping (list of (H,W,4) arrays), the timing getters.  Differences: numpy arrays are
 // taken with bulk copies instead of per-element loops, and two additional *Flat entry points return
 // whole (N, M, 3) arrays for large particle counts (a Python list of 64 M dicts is not an option).
-// Not bound (out of the hot path): MPASOReader file ingestion, MOPS_RunReGrid.
+// Not bound (out of the hot path): MOPS_RunReGrid.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -87,8 +87,39 @@ PYBIND11_MODULE(pyMOPS, m)
         .value("kZTop", MOPS::AttributeType::kZTop).value("kLayerThickness", MOPS::AttributeType::kLayerThickness)
         .value("kBottomDepth", MOPS::AttributeType::kBottomDepth);
 
+    py::class_<MOPS::MPASOReader, std::shared_ptr<MOPS::MPASOReader>>(m, "MPASOReader")
+        .def(py::init<>())
+        .def_static("readGridData", &MOPS::MPASOReader::readGridData, py::arg("yaml_path"))
+        .def_static("readSolData", &MOPS::MPASOReader::readSolData, py::arg("yaml_path"), py::arg("time_str"), py::arg("time_index") = 0);
+
     py::class_<MOPS::MPASOGrid, std::shared_ptr<MOPS::MPASOGrid>>(m, "MPASOGrid")
         .def(py::init<>())
+        .def("init_from_reader", [](MOPS::MPASOGrid& self, const std::shared_ptr<MOPS::MPASOReader>& reader) { self.initGrid(reader.get()); })
+        // read-back of the arrays (numpy copies), e.g. to check what a reader delivered
+        .def("getArray", [](const MOPS::MPASOGrid& g, const std::string& name) -> py::object {
+            auto v3 = [](const std::vector<vec3>& v) {
+                py::array_t<double> a({static_cast<py::ssize_t>(v.size()), py::ssize_t(3)});
+                if (!v.empty()) std::memcpy(a.mutable_data(), v.data(), v.size() * sizeof(vec3));
+                return py::object(a);
+            };
+            auto sz = [](const std::vector<size_t>& v) {
+                py::array_t<int64_t> a(static_cast<py::ssize_t>(v.size()));
+                for (size_t i = 0; i < v.size(); ++i) a.mutable_data()[i] = static_cast<int64_t>(v[i]);
+                return py::object(a);
+            };
+            if (name == "cellCoord") return v3(g.cellCoord_vec);
+            if (name == "vertexCoord") return v3(g.vertexCoord_vec);
+            if (name == "verticesOnCell") return sz(g.verticesOnCell_vec);
+            if (name == "cellsOnCell") return sz(g.cellsOnCell_vec);
+            if (name == "cellsOnVertex") return sz(g.cellsOnVertex_vec);
+            if (name == "nEdgesOnCell") return sz(g.numberVertexOnCell_vec);
+            if (name == "refBottomDepth") return py::object(py::array_t<double>(static_cast<py::ssize_t>(g.cellRefBottomDepth_vec.size()), g.cellRefBottomDepth_vec.data()));
+            throw std::runtime_error("unknown grid array " + name);
+        })
+        .def_readonly("mCellsSize", &MOPS::MPASOGrid::mCellsSize)
+        .def_readonly("mVertexSize", &MOPS::MPASOGrid::mVertexSize)
+        .def_readonly("mMaxEdgesSize", &MOPS::MPASOGrid::mMaxEdgesSize)
+        .def_readonly("mMeshName", &MOPS::MPASOGrid::mMeshName)
         .def("setGridAttribute", &MOPS::MPASOGrid::setGridAttribute)
         .def("setGridAttributesVec3", [](MOPS::MPASOGrid& self, MOPS::GridAttributeType type, arr_d arr) {
             self.setGridAttributesVec3(type, to_vec3(arr, "Input array"));
@@ -112,6 +143,21 @@ PYBIND11_MODULE(pyMOPS, m)
 
     py::class_<MOPS::MPASOSolution, std::shared_ptr<MOPS::MPASOSolution>>(m, "MPASOSolution")
         .def(py::init<>())
+        .def("init_from_reader", [](MOPS::MPASOSolution& self, const std::shared_ptr<MOPS::MPASOReader>& reader) { self.initSolution(reader.get()); })
+        .def("add_attribute", &MOPS::MPASOSolution::addAttribute)
+        .def("getArray", [](const MOPS::MPASOSolution& s, const std::string& name) -> py::object {
+            auto d = [](const std::vector<double>& v) { return py::object(py::array_t<double>(static_cast<py::ssize_t>(v.size()), v.data())); };
+            if (name == "velocityZonal") return d(s.cellZonalVelocity_vec);
+            if (name == "velocityMeridional") return d(s.cellMeridionalVelocity_vec);
+            if (name == "layerThickness") return d(s.cellLayerThickness_vec);
+            if (name == "bottomDepth") return d(s.cellBottomDepth_vec);
+            if (name == "vertVelocityTop") return d(s.cellVertVelocity_vec);
+            auto it = s.mDoubleAttributes.find(name);
+            if (it != s.mDoubleAttributes.end()) return d(it->second);
+            throw std::runtime_error("unknown solution array " + name);
+        })
+        .def_readonly("mVertLevels", &MOPS::MPASOSolution::mVertLevels)
+        .def_readonly("mDataName", &MOPS::MPASOSolution::mDataName)
         .def("setTimestep", &MOPS::MPASOSolution::setTimestep)
         .def("setAttribute", &MOPS::MPASOSolution::setAttribute)
         .def("setAttributesDouble", [](MOPS::MPASOSolution& self, MOPS::AttributeType type, arr_d arr) {

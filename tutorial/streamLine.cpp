@@ -1,7 +1,9 @@
 // tutorial/streamLine.cpp -- the reference's streamline tutorial (tutorial/streamLine.cpp:12-103 of
 // YosefQiu/MOPS) on a synthetic fixture: same API call sequence, BASELINE config C1 parameters
 // (100 uniform seeds, depth 800 m, dt = 120 s, 1 day, RK4).
-//   usage: streamLine <fixture.bin> <lines_out.bin>
+//   usage: streamLine <fixture.bin | stream.yaml> <lines_out.bin> [date-tag]
+// With a YAML stream description the grid and the solution come from MPAS NetCDF-3 files through
+// MPASOReader, exactly as in the reference tutorial (tutorial/streamLine.cpp:72-103).
 #include "api/MOPS.h"
 #include "fixture.hpp"
 
@@ -13,7 +15,21 @@ int main(int argc, char** argv)
         std::cerr << "usage: streamLine <fixture.bin> <lines_out.bin>\n";
         return 2;
     }
-    auto fx = fixture::load(argv[1]);
+    const std::string input = argv[1];
+    fixture::Loaded fx;
+    if (input.size() > 5 && input.substr(input.size() - 5) == ".yaml") {
+        const std::string timeStamp = argc > 3 ? argv[3] : "0001-01-01";
+        auto grid = std::make_shared<MOPS::MPASOGrid>();
+        auto sol = std::make_shared<MOPS::MPASOSolution>();
+        sol->initSolution(MOPS::MPASOReader::readSolData(input, timeStamp, 0).get());
+        sol->addAttribute("temperature", MOPS::AttributeFormat::kFloat);
+        sol->addAttribute("salinity", MOPS::AttributeFormat::kFloat);
+        grid->initGrid(MOPS::MPASOReader::readGridData(input).get());
+        fx.grid = grid;
+        fx.sols.push_back(sol);
+    } else {
+        fx = fixture::load(input);
+    }
 
     MOPS::MOPS_Init("gpu");
     MOPS::MOPS_Begin();
