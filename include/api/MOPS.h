@@ -269,6 +269,11 @@ public:
     std::vector<TrajectoryLine> runStreamLine(TrajectorySettings* config, std::vector<CartesianCoord>& sample_points);
     std::vector<TrajectoryLine> runPathLine(TrajectorySettings* config, std::vector<CartesianCoord>& sample_points);
     std::vector<ImageBuffer<double>> runRemapping(VisualizationSettings* config);
+    // depth-vs-longitude section at config->FixedLatitude; rows span refBottomDepth.front()..back()
+    // (src/Core/MOPSApp.cpp:198-210 -> VisualizeFixedLatitude)
+    ImageBuffer<double> runReGrid(VisualizationSettings* config);
+    // velocity of layer config->FixedLayer (MPASOVisualizer::VisualizeFixedLayer, src/Core/MPASOVisualizer.cpp:17-20)
+    ImageBuffer<double> runFixedLayer(VisualizationSettings* config);
     void generateSamplePoints(SamplingSettings* config, std::vector<CartesianCoord>& sample_points);
     void generateSamplePointsAtCenter(SamplingSettings* config, std::vector<CartesianCoord>& sample_points);
     MOPSState getState() const { return mState; }

@@ -222,6 +222,24 @@ typedef struct mops_remap_stats {
 int mops_remap_fixed_depth(mops_ctx* ctx, const mops_remap_cfg* cfg, int32_t slot,
                            double* img0, double* img1, int32_t* pixel_cell, mops_remap_stats* stats);
 
+/* ---- the two other views of the reference ---------------------------------- */
+typedef struct mops_view_cfg {
+    int32_t width, height;      /* VisualizationSettings::imageSize                                   */
+    double lat_min, lat_max;    /* fixed layer: LatRange                                              */
+    double lon_min, lon_max;    /* LonRange (fixed latitude: inclusive end points, VK:513-514)        */
+    int32_t fixed_layer;        /* fixed layer: FixedLayer, clamped to [0, nLevels-1] as ClampLayer   */
+    int32_t mem;                /* MOPS_MEM_* of img / pixel_cell                                     */
+    double fixed_latitude;      /* fixed latitude [deg]                                               */
+    double depth_min, depth_max;/* fixed latitude: refBottomDepth.front() / .back() (row 0 / last row) */
+} mops_view_cfg;
+/* replaces MOPS::Factory::VisualizeFixedLayer (src/Common/MOPSFactory.h:9-13 -> VK:141-236) */
+int mops_remap_fixed_layer(mops_ctx* ctx, const mops_view_cfg* cfg, int32_t slot, double* img, int32_t* pixel_cell,
+                           mops_remap_stats* stats);
+/* replaces MOPS::Factory::VisualizeFixedLatitude = MOPSApp::runReGrid
+ * (src/Common/MOPSFactory.h:21-26 -> VK:473-651; host loops only in the reference's CUDA backend) */
+int mops_regrid_fixed_latitude(mops_ctx* ctx, const mops_view_cfg* cfg, int32_t slot, double* img, int32_t* pixel_cell,
+                               mops_remap_stats* stats);
+
 /* ---- introspection ---------------------------------------------------------------- */
 typedef struct mops_info {
     int32_t device, sm_count, cc_major, cc_minor;

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "mops_abi_version", "mops_create", "mops_destroy", "mops_last_error", "mops_host_alloc", "mops_host_free",
     "mops_synchronize", "mops_set_stream", "mops_mark", "mops_elapsed_ms", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait",
     "mops_get_prepared", "mops_locate", "mops_streamline", "mops_pathline", "mops_finalize_lines",
-    "mops_remap_fixed_depth", "mops_get_info",
+    "mops_remap_fixed_depth", "mops_remap_fixed_layer", "mops_regrid_fixed_latitude", "mops_get_info",
 ]
 
 
@@ -56,6 +56,12 @@ class RemapCfg(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("lat_min", C.c_double), ("lat_max", C.c_double),
                 ("lon_min", C.c_double), ("lon_max", C.c_double), ("fixed_depth", C.c_double), ("mem", C.c_int32),
                 ("reserved", C.c_int32 * 3)]
+
+
+class ViewCfg(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("lat_min", C.c_double), ("lat_max", C.c_double),
+                ("lon_min", C.c_double), ("lon_max", C.c_double), ("fixed_layer", C.c_int32), ("mem", C.c_int32),
+                ("fixed_latitude", C.c_double), ("depth_min", C.c_double), ("depth_max", C.c_double)]
 
 
 class RemapStats(C.Structure):
@@ -105,6 +111,8 @@ def load_library():
     lib.mops_pathline.argtypes = [vp, C.POINTER(TrajCfg), i32, i32, C.POINTER(TrajIO), C.POINTER(TrajStats)]
     lib.mops_finalize_lines.argtypes = [i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.mops_remap_fixed_depth.argtypes = [vp, C.POINTER(RemapCfg), i32, vp, vp, vp, C.POINTER(RemapStats)]
+    lib.mops_remap_fixed_layer.argtypes = [vp, C.POINTER(ViewCfg), i32, vp, vp, C.POINTER(RemapStats)]
+    lib.mops_regrid_fixed_latitude.argtypes = [vp, C.POINTER(ViewCfg), i32, vp, vp, C.POINTER(RemapStats)]
     lib.mops_get_info.argtypes = [vp, C.POINTER(Info)]
     _lib = lib
     return lib
@@ -305,6 +313,20 @@ class Engine:
         st = RemapStats()
         self._ck(self.lib.mops_remap_fixed_depth(self.h, C.byref(cfg), slot, _ptr(img0), _ptr(img1), _ptr(cells), C.byref(st)))
         return {"img0": img0, "img1": img1 if st.n_images > 1 else None, "pixel_cell": cells, "stats": st}
+
+    def remap_fixed_layer(self, slot, width, height, layer, lat_range=(-90.0, 90.0), lon_range=(-180.0, 180.0)):
+        img = np.zeros((height, width, 4)); cells = np.zeros((height, width), dtype=np.int32)
+        cfg = ViewCfg(width, height, lat_range[0], lat_range[1], lon_range[0], lon_range[1], int(layer), MEM_HOST, 0.0, 0.0, 0.0)
+        st = RemapStats()
+        self._ck(self.lib.mops_remap_fixed_layer(self.h, C.byref(cfg), slot, _ptr(img), _ptr(cells), C.byref(st)))
+        return {"img": img, "pixel_cell": cells, "stats": st}
+
+    def regrid_fixed_latitude(self, slot, width, height, latitude, depth_min, depth_max, lon_range=(-180.0, 180.0)):
+        img = np.zeros((height, width, 4)); cells = np.zeros((height, width), dtype=np.int32)
+        cfg = ViewCfg(width, height, 0.0, 0.0, lon_range[0], lon_range[1], 0, MEM_HOST, float(latitude), float(depth_min), float(depth_max))
+        st = RemapStats()
+        self._ck(self.lib.mops_regrid_fixed_latitude(self.h, C.byref(cfg), slot, _ptr(img), _ptr(cells), C.byref(st)))
+        return {"img": img, "pixel_cell": cells, "stats": st}
 
     def remap_device(self, slot, cfg: RemapCfg, img0, img1=None, cells=None, want_stats=True):
         st = RemapStats()

@@ -605,6 +605,81 @@ void launch_remap(mops_ctx* ctx, const RemapParams& P)
     ctx->launches++;
 }
 
+template <int M>
+void launch_view(mops_ctx* ctx, const ViewParams& P, int mode)
+{
+    const int grid = blocks_for((long long)P.width * P.height, 128);
+    if (mode == 0) k_view<M, 0><<<grid, 128, 0, ctx->stream>>>(P);
+    else k_view<M, 1><<<grid, 128, 0, ctx->stream>>>(P);
+    ctx->launches++;
+}
+
+int view_impl(mops_ctx* ctx, const mops_view_cfg* cfg, int slot, double* img, int* pixel_cell, mops_remap_stats* stats, int mode)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (!cfg || !img) return fail(ctx, MOPS_E_INVALID, "null cfg/img");
+    if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "no mesh");
+    if (slot < 0 || slot >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[slot].valid) return fail(ctx, MOPS_E_STATE, "snapshot slot %d not set", slot);
+    if (cfg->width <= 0 || cfg->height <= 0) return fail(ctx, MOPS_E_INVALID, "invalid image size"); // VK:160-163, 483-486
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = wait_slot(ctx, slot))) return rc;
+    Snapshot& S = ctx->snap[slot];
+    const size_t npx = (size_t)cfg->width * cfg->height;
+    const bool host = (cfg->mem == MOPS_MEM_HOST);
+    const long long launches0 = ctx->launches;
+    cudaStream_t st = ctx->stream;
+    double* d0;
+    int* dc = nullptr;
+    CK(cudaEventRecord(ctx->ev0, st));
+    if (host) {
+        if ((rc = ensure(ctx, ctx->r_img0, npx * 32))) return rc;
+        d0 = (double*)ctx->r_img0.p;
+        if (pixel_cell) { if ((rc = ensure(ctx, ctx->r_cells, npx * 4))) return rc; dc = (int*)ctx->r_cells.p; }
+    } else {
+        d0 = img; dc = pixel_cell;
+    }
+    CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
+    ViewParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.rec = ctx->rec; P.c4 = ctx->c4; P.cube = ctx->cube; P.c_int2ext = ctx->c_int2ext; P.F = ctx->F; P.nC = ctx->nC; P.L = S.L;
+    P.s = view_of(S);
+    P.width = cfg->width; P.height = cfg->height;
+    P.minLat = cfg->lat_min; P.maxLat = cfg->lat_max; P.minLon = cfg->lon_min; P.maxLon = cfg->lon_max;
+    P.fixed_layer = std::min(std::max(cfg->fixed_layer, 0), S.L - 1); // ClampLayer, VK:14-26
+    P.fixed_lat = cfg->fixed_latitude; P.minDepth = cfg->depth_min; P.maxDepth = cfg->depth_max;
+    P.img = d0; P.pixel_cell = dc; P.nan_count = ctx->counters + 2;
+    CK(cudaEventRecord(ctx->ev1, st));
+    switch (ctx->M) {
+    case 6: launch_view<6>(ctx, P, mode); break;
+    case 8: launch_view<8>(ctx, P, mode); break;
+    default: launch_view<20>(ctx, P, mode); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev2, st));
+    if ((rc = mark_use(ctx, slot))) return rc;
+    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    if (host) {
+        CK(cudaMemcpyAsync(img, d0, npx * 32, cudaMemcpyDeviceToHost, st));
+        if (dc) CK(cudaMemcpyAsync(pixel_cell, dc, npx * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (host || stats) {
+        CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev3, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2) == cudaSuccess) stats->kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3) == cudaSuccess) stats->total_ms = ms;
+        stats->nan_pixels = (int64_t)h_counters[2];
+        stats->launches = (int32_t)(ctx->launches - launches0);
+        stats->n_images = 1;
+    }
+    return MOPS_OK;
+}
+
 } // namespace
 
 // =========================================================================================
@@ -1065,6 +1140,18 @@ int mops_finalize_lines(int64_t n, int32_t each, const double* seeds, const doub
         if (last) std::memcpy(last + 3 * i, P + 3 * (per - 1), 24);
     }
     return MOPS_OK;
+}
+
+int mops_remap_fixed_layer(mops_ctx* ctx, const mops_view_cfg* cfg, int32_t slot, double* img, int32_t* pixel_cell,
+                           mops_remap_stats* stats)
+{
+    return view_impl(ctx, cfg, slot, img, pixel_cell, stats, 0);
+}
+
+int mops_regrid_fixed_latitude(mops_ctx* ctx, const mops_view_cfg* cfg, int32_t slot, double* img, int32_t* pixel_cell,
+                               mops_remap_stats* stats)
+{
+    return view_impl(ctx, cfg, slot, img, pixel_cell, stats, 1);
 }
 
 int mops_get_info(mops_ctx* ctx, mops_info* out)

@@ -78,9 +78,9 @@ __device__ __noinline__ double min_edge_angle(const CellRec<M>* __restrict__ rec
     return best;
 }
 
+// TBBKernel::IsInMesh on the precomputed edge normals (TK:21-54)
 template <int M>
-__device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
-                                             double (&w)[M], bool& wfinite)
+__device__ __forceinline__ bool in_mesh(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz)
 {
     if (!finite3(px, py, pz)) return false; // TK:29-33
     bool inside = true;
@@ -91,8 +91,15 @@ __device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec,
             if (direction < 0.0) inside = false;
         }
     }
-    if (!inside) return false;
+    return inside;
+}
 
+// Interpolator::CalcPolygonWachspress (src/Utils/Interpolation.hpp:137-165) with the corner areas B_i
+// taken from the record.  wfinite: all weights finite (a point exactly on an edge gives inf/NaN, N7).
+template <int M>
+__device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
+                                                   double (&w)[M], bool& wfinite)
+{
     double ax[M], ay[M], az[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) {
@@ -131,6 +138,15 @@ __device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec,
     for (int i = 0; i < M; ++i)
         if (i < nv) w[i] *= recp;
     wfinite = isfinite(sum) && isfinite(recp) && (sum > 0.0);
+}
+
+// returns false when the point is not in the cell (IsInMesh); else fills the normalised weights
+template <int M>
+__device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
+                                             double (&w)[M], bool& wfinite)
+{
+    if (!in_mesh<M>(rec, nv, px, py, pz)) return false;
+    wachspress_weights<M>(rec, nv, px, py, pz, w, wfinite);
     return true;
 }
 
@@ -293,6 +309,44 @@ __device__ __noinline__ LayerRes slow_layer_remap(const CellRec<M>* __restrict__
     if (DEPTH <= col[0]) r.layer = 0;
     if (r.layer < 0) return r;
     r.top = col[(r.layer - 1 > 0) ? r.layer - 1 : 0];
+    r.bot = col[r.layer];
+    return r;
+}
+
+// fixed-latitude section (VisualizeFixedLatitude) column logic on the fixed-up column, VK:566-604:
+// range test and first-match scan with EPSILON = 1e-6; layer = -1: outside / none.
+template <int M>
+__device__ __noinline__ LayerRes slow_layer_latitude(const CellRec<M>* __restrict__ rec, const double* __restrict__ ztop, int L,
+                                                     double px, double py, double pz, double DEPTH)
+{
+    double col[100];
+    // the reference computes these weights WITHOUT the IsInMesh gate (it used isOnOcean before)
+    {
+        double w[M];
+        bool wfinite;
+        const int nv = rec->nv;
+        wachspress_weights<M>(rec, nv, px, py, pz, w, wfinite);
+        for (int k = 0; k < L; ++k) {
+            double z = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+                if (i < nv) z += w[i] * ztop[rec->vid[i] * L + k];
+            col[k] = z;
+        }
+        for (int k = 1; k < L; ++k)
+            if (col[k] > col[k - 1]) col[k] = col[k - 1] - 1e-9;
+    }
+    const double EPS = 1e-6;
+    LayerRes r;
+    r.layer = -1; r.top = 0.0; r.bot = 0.0;
+    if (DEPTH > col[0] + EPS || DEPTH < col[L - 1] - EPS) return r;
+    for (int k = 1; k < L; ++k) {
+        double zu = col[k - 1], zd = col[k];
+        if (zu < zd) { const double t = zu; zu = zd; zd = t; }
+        if (DEPTH <= zu + EPS && DEPTH >= zd - EPS) { r.layer = k; break; }
+    }
+    if (r.layer < 0) return r;
+    r.top = col[r.layer - 1];
     r.bot = col[r.layer];
     return r;
 }

@@ -681,4 +681,158 @@ __global__ void __launch_bounds__(128) k_remap(const RemapParams P)
     }
 }
 
+// =========================================================================================
+// the two other lat/lon views of the reference, same locate + Wachspress + gather
+// building blocks, one thread per pixel:
+//   MODE 0  VisualizeFixedLayer    VK:141-236   velocity of ONE layer -> ENU, pixel (u_east, v_north, 0, 1)
+//   MODE 1  VisualizeFixedLatitude VK:473-651   depth-vs-longitude section at a fixed latitude
+//           (host loops only in the reference's CUDA backend)
+// =========================================================================================
+struct ViewParams {
+    const void* rec;
+    const double4* c4;
+    const int* cube;
+    const int* c_int2ext;
+    int F, nC, L;
+    SnapView s;
+    int width, height;
+    double minLat, maxLat, minLon, maxLon; // MODE 0 pixel -> lat/lon as in k_remap
+    int fixed_layer;                       // MODE 0 (already clamped to [0, L-1])
+    double fixed_lat, minDepth, maxDepth;  // MODE 1: refBottomDepth front / back
+    double* img;
+    int* pixel_cell;
+    unsigned long long* nan_count;
+};
+
+template <int M, int MODE>
+__global__ void __launch_bounds__(128) k_view(const ViewParams P)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.width * P.height) return;
+    const int ih = (int)(gid / P.width);
+    const int jw = (int)(gid % P.width);
+    const double rr = 6371010.0;
+    double lat, lon, DEPTH = 0.0;
+    if (MODE == 0) {
+        lat = P.maxLat - ((double)ih / (double)P.height * (P.maxLat - P.minLat));
+        lon = ((double)jw / (double)P.width * (P.maxLon - P.minLon)) + P.minLon;
+        lat = lat * (3.14159265358979323846 / 180.0);
+        lon = lon * (3.14159265358979323846 / 180.0);
+    } else {
+        const double i_step = (P.height > 1) ? (P.maxDepth - P.minDepth) / (P.height - 1) : 0.0; // VK:513-514
+        const double j_step = (P.width > 1) ? (P.maxLon - P.minLon) / (P.width - 1) : 0.0;
+        const double depth_plot = P.minDepth + ih * i_step;
+        DEPTH = -fabs(depth_plot);
+        lat = P.fixed_lat * (3.14159265358979323846 / 180.0);
+        lon = (P.minLon + jw * j_step) * (3.14159265358979323846 / 180.0);
+    }
+    double sintheta, costheta, sinphi, cosphi;
+    sincos(lat, &sintheta, &costheta);
+    sincos(lon, &sinphi, &cosphi);
+    d3 pos;
+    pos.x = rr * costheta * cosphi;
+    pos.y = rr * costheta * sinphi;
+    pos.z = rr * sintheta;
+
+    const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
+    int cell = -1;
+    if (finite3(pos.x, pos.y, pos.z)) cell = walk_nearest<M>(recs, P.c4, P.cube[cube_bucket(pos.x, pos.y, pos.z, P.F)], pos.x, pos.y, pos.z);
+    if (P.pixel_cell) P.pixel_cell[gid] = cell >= 0 ? P.c_int2ext[cell] : -1;
+
+    bool ok = (cell >= 0 && cell < P.nC);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (ok) {
+        const CellRec<M>* __restrict__ rec = recs + cell;
+        const int nv = rec->nv;
+        const int L = P.L;
+        ok = nv > 0;
+        if (ok) {
+            if (MODE == 0) {
+                ok = in_mesh<M>(rec, nv, pos.x, pos.y, pos.z);
+            } else {
+                // MPASOField::isOnOcean (src/Core/MPASOField.cpp:36-81): dot(cross(A,B), p - A) must have
+                // one sign for every edge (cross(O-A, O-B) == cross(A,B) bit for bit)
+                bool first_pos = false, land = false;
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    if (k < nv) {
+                        const double dir = rec->nx[k] * (pos.x - rec->vx[k]) + rec->ny[k] * (pos.y - rec->vy[k]) + rec->nz[k] * (pos.z - rec->vz[k]);
+                        const bool positive = dir > 0;
+                        if (k == 0) first_pos = positive;
+                        else if (positive != first_pos) land = true;
+                    }
+                }
+                ok = !land;
+            }
+        }
+        if (ok) {
+            double w[M];
+            bool wfinite = false;
+            wachspress_weights<M>(rec, nv, pos.x, pos.y, pos.z, w, wfinite);
+            int vo[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+            double dummy;
+            if (MODE == 0) {
+                gather_velw<M>(P.s.velw, vo, w, nv, P.fixed_layer, fx, fy, fz, dummy); // VK:220-226
+            } else {
+                // column + fix-up (VK:566-582), range test and first-match scan with EPSILON = 1e-6 (VK:584-604)
+                const double EPS = 1e-6;
+                int layer = -1;
+                double z_up = 0.0, z_dn = 0.0;
+                if ((P.s.mono[cell] != 0) && wfinite) {
+                    const ZCol<M> z{P.s.ztop, w, vo, nv, L};
+                    if (DEPTH > z(0) + EPS || DEPTH < z(L - 1) - EPS) ok = false;
+                    if (ok) {
+                        // non-increasing column: first k with DEPTH >= z[k] - EPS (DEPTH <= z[k-1] + EPS then holds)
+                        int lo = 1, hi = L - 1;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (DEPTH >= z(mid) - EPS) hi = mid;
+                            else lo = mid + 1;
+                        }
+                        layer = lo;
+                        z_up = z(layer - 1);
+                        z_dn = z(layer);
+                    }
+                } else {
+                    const LayerRes lr = slow_layer_latitude<M>(rec, P.s.ztop, L, pos.x, pos.y, pos.z, DEPTH);
+                    layer = lr.layer; z_up = lr.top; z_dn = lr.bot;
+                    if (layer < 0) ok = false;
+                }
+                if (ok) {
+                    if (z_up < z_dn) { const double t = z_up; z_up = z_dn; z_dn = t; }
+                    const double denom = z_up - z_dn;
+                    if (fabs(denom) < 1e-30) ok = false; // VK:616-620
+                    if (ok) {
+                        const double t = (DEPTH - z_dn) / denom; // not clamped (VK:622)
+                        double ux, uy, uz, dx, dy, dz;
+                        gather_velw<M>(P.s.velw, vo, w, nv, layer - 1, ux, uy, uz, dummy);
+                        gather_velw<M>(P.s.velw, vo, w, nv, layer, dx, dy, dz, dummy);
+                        const double omt = 1.0 - t;
+                        fx = omt * dx + t * ux; // VK:641
+                        fy = omt * dy + t * uy;
+                        fz = omt * dz + t * uz;
+                    }
+                }
+            }
+        }
+    }
+    if (ok) {
+        double u_east = 0.0, v_north = 0.0;
+        if (!(pos.x == 0.0 && pos.y == 0.0)) { // GeoConverter::convertXYZVelocityToENU
+            const double Rxy = sqrt(pos.x * pos.x + pos.y * pos.y);
+            const double Rxyz = sqrt(pos.x * pos.x + pos.y * pos.y + pos.z * pos.z);
+            const double slon = pos.y / Rxy, clon = pos.x / Rxy, slat = pos.z / Rxyz, clat = Rxy / Rxyz;
+            u_east = -slon * fx + clon * fy;
+            v_north = -slat * (clon * fx + slon * fy) + clat * fz;
+        }
+        put_pixel(P.img, gid, u_east, v_north, 0.0);
+    } else {
+        const double nanv = nan("");
+        put_pixel(P.img, gid, nanv, nanv, nanv);
+        if (P.nan_count) atomicAdd(P.nan_count, 1ull);
+    }
+}
+
 } // namespace mops

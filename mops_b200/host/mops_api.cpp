@@ -5,6 +5,10 @@
 #include "api/MOPS.h"
 #include "mops_b200.h"
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -188,25 +192,44 @@ MOPSApp::~MOPSApp()
     if (mCtx) mops_destroy(mCtx);
 }
 
+namespace {
+void segv_backtrace(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "[MOPS/b200] fatal signal, native backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+} // namespace
+
 void MOPSApp::init(const char* device)
 {
-    std::cout << " [ system information ]\n";
+    if (std::getenv("MOPS_BACKTRACE")) { // debugging aid: native frames on SIGSEGV / SIGABRT
+        signal(SIGSEGV, segv_backtrace);
+        signal(SIGABRT, segv_backtrace);
+    }
+    std::printf(" [ system information ]\n");
     if (device && std::strcmp(device, "cpu") == 0)
-        std::cout << "Device requested: cpu -- this build has no CPU path; using the CUDA device\n";
+        std::printf("Device requested: cpu -- this build has no CPU path; using the CUDA device\n");
     int dev = 0;
     if (const char* e = std::getenv("MOPS_DEVICE")) dev = std::atoi(e);
     if (!mCtx) {
         const int rc = mops_create(&mCtx, dev);
         if (rc != MOPS_OK) {
-            std::cerr << " [ MOPS: no usable CUDA device (mops_create -> " << rc << "); there is no CPU fallback ]\n";
+            std::fprintf(stderr, " [ MOPS: no usable CUDA device (mops_create -> %d); there is no CPU fallback ]\n", rc);
             std::exit(1);
         }
     }
     mops_info info;
+    std::memset(&info, 0, sizeof(info));
     mops_get_info(mCtx, &info);
-    std::cout << "Device selected : CUDA device " << info.device << " (sm_" << info.cc_major << info.cc_minor << ", " << info.sm_count
-              << " SMs) -- B200-native engine\n";
-    std::cout << "MOPS Version    : mops-b200 (ABI " << mops_abi_version() << ")\n";
+    std::printf("Device selected : CUDA device %d (sm_%d%d, %d SMs) -- B200-native engine\n", info.device, info.cc_major, info.cc_minor,
+                info.sm_count);
+    std::printf("MOPS Version    : mops-b200 (ABI %d)\n", mops_abi_version());
+    std::fflush(stdout);
     mpasoGrid = std::make_shared<MPASOGrid>();
 }
 
@@ -296,7 +319,7 @@ int MOPSApp::residentSlot(int solID)
     const size_t nC = static_cast<size_t>(mpasoGrid->mCellsSize), L = static_cast<size_t>(s.mVertLevels);
     if (s.cellZonalVelocity_vec.size() < nC * L || s.cellMeridionalVelocity_vec.size() < nC * L ||
         s.cellLayerThickness_vec.size() < nC * L || s.cellBottomDepth_vec.size() < nC) {
-        std::cerr << "[MOPSApp]::solution " << solID << ": zonal/meridional velocity, layerThickness and bottomDepth are required\n";
+        std::fprintf(stderr, "[MOPSApp]::solution %d: zonal/meridional velocity, layerThickness and bottomDepth are required\n", solID);
         std::exit(1);
     }
     // scalar attributes in std::map (alphabetical) order, first two (R11)
@@ -502,6 +525,66 @@ std::vector<ImageBuffer<double>> MOPSApp::runRemapping(VisualizationSettings* co
         book().add("MemoryCopy::Remapping", 3, st.total_ms - st.kernel_ms);
     }
     return img_vec;
+}
+
+namespace {
+mops_view_cfg make_view_cfg(const VisualizationSettings* config)
+{
+    mops_view_cfg cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.width = static_cast<int>(config->imageSize.x());
+    cfg.height = static_cast<int>(config->imageSize.y());
+    cfg.lat_min = config->LatRange.x(); cfg.lat_max = config->LatRange.y();
+    cfg.lon_min = config->LonRange.x(); cfg.lon_max = config->LonRange.y();
+    cfg.mem = MOPS_MEM_HOST;
+    return cfg;
+}
+} // namespace
+
+ImageBuffer<double> MOPSApp::runReGrid(VisualizationSettings* config)
+{
+    Scope sc("GPUKernel::ReGrid", 6);
+    const int w = config ? static_cast<int>(config->imageSize.x()) : 0, h = config ? static_cast<int>(config->imageSize.y()) : 0;
+    ImageBuffer<double> img(std::max(w, 0), std::max(h, 0));
+    if (!config || !mpasoField || !mpasoField->mSol_Front) {
+        std::fprintf(stderr, "[B200::VisualizeFixedLatitude] invalid inputs\n");
+        return img;
+    }
+    if (w <= 0 || h <= 0) {
+        std::fprintf(stderr, "[B200::VisualizeFixedLatitude] invalid image size\n"); // VK:483-486
+        return img;
+    }
+    if (mpasoGrid->cellRefBottomDepth_vec.empty()) {
+        std::fprintf(stderr, "[B200::VisualizeFixedLatitude] refBottomDepth is empty\n"); // VK:491-495
+        return img;
+    }
+    mops_view_cfg cfg = make_view_cfg(config);
+    cfg.fixed_latitude = config->FixedLatitude;
+    cfg.depth_min = mpasoGrid->cellRefBottomDepth_vec.front();
+    cfg.depth_max = mpasoGrid->cellRefBottomDepth_vec.back();
+    mops_remap_stats st;
+    const int rc = mops_regrid_fixed_latitude(mCtx, &cfg, residentSlot(mFrontID), img.mPixels.data(), nullptr, &st);
+    if (rc != MOPS_OK) engine_error(mCtx, "runReGrid", rc);
+    else book().add("GPUKernel::ReGrid::kernel", 4, st.kernel_ms);
+    return img;
+}
+
+ImageBuffer<double> MOPSApp::runFixedLayer(VisualizationSettings* config)
+{
+    Scope sc("GPUKernel::FixedLayer", 6);
+    const int w = config ? static_cast<int>(config->imageSize.x()) : 0, h = config ? static_cast<int>(config->imageSize.y()) : 0;
+    ImageBuffer<double> img(std::max(w, 0), std::max(h, 0));
+    if (!config || !mpasoField || !mpasoField->mSol_Front || w <= 0 || h <= 0) {
+        std::fprintf(stderr, "[B200::VisualizeFixedLayer] invalid inputs\n"); // VK:143-163
+        return img;
+    }
+    mops_view_cfg cfg = make_view_cfg(config);
+    cfg.fixed_layer = static_cast<int>(config->FixedLayer); // ClampLayer(int) takes the truncated double
+    mops_remap_stats st;
+    const int rc = mops_remap_fixed_layer(mCtx, &cfg, residentSlot(mFrontID), img.mPixels.data(), nullptr, &st);
+    if (rc != MOPS_OK) engine_error(mCtx, "runFixedLayer", rc);
+    else book().add("GPUKernel::FixedLayer::kernel", 4, st.kernel_ms);
+    return img;
 }
 
 void MOPSApp::generateSamplePoints(SamplingSettings* config, std::vector<CartesianCoord>& points)

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <iostream>
 
 namespace MOPS {
@@ -110,7 +111,7 @@ MPASOReader::Ptr MPASOReader::readSolData(const std::string& yaml_path, const st
             std::exit(-1);
         }
         if (timestep < 0) {
-            std::cerr << "[MPASOReader]::Error: Invalid timestep index " << timestep << std::endl;
+            std::fprintf(stderr, "[MPASOReader]::Error: Invalid timestep index %d\n", timestep);
             std::exit(-1);
         }
         const int fi = static_cast<int>(std::distance(sub->filenames.begin(), it));

@@ -1111,6 +1111,128 @@ int orc_remap_fixed_depth(int n_cells, int n_vertices, int max_edges, int L,
 }
 
 /* ------------------------------------------------------------------------------------- */
+/* 8f-3: VisualizeFixedLayer (VK:141-236) and VisualizeFixedLatitude (VK:473-651)            */
+/* ------------------------------------------------------------------------------------- */
+int orc_remap_fixed_layer(int n_cells, int n_vertices, int max_edges, int L,
+                          const double* cell_xyz, const double* vertex_xyz, const int32_t* voc, const int32_t* coc, const int32_t* nedges,
+                          const double* vel_v, int width, int height, double minLat, double maxLat, double minLon, double maxLon,
+                          int fixed_layer_in, double* img, int32_t* pixel_cell)
+{
+    orc_mesh m = {n_cells, n_vertices, max_edges, L, cell_xyz, vertex_xyz, voc, coc, nedges};
+    int fixed_layer = fixed_layer_in; /* ClampLayer, VK:14-26 */
+    if (L <= 0) fixed_layer = 0;
+    else if (fixed_layer < 0) fixed_layer = 0;
+    else if (fixed_layer >= L) fixed_layer = L - 1;
+    orc_bins* bins = bins_build(n_cells, cell_xyz);
+    for (int64_t gid = 0; gid < (int64_t)width * height; ++gid) {
+        const int ih = (int)(gid / width), jw = (int)(gid % width);
+        double pp[3];
+        orc_pixel_position(width, height, minLat, maxLat, minLon, maxLon, ih, jw, pp);
+        v3 pos = v3_make(pp[0], pp[1], pp[2]);
+        const int cell_id = bins_nearest(bins, n_cells, cell_xyz, pp);
+        if (pixel_cell) pixel_cell[gid] = cell_id;
+        int ok = !(cell_id < 0 || cell_id >= n_cells);
+        int nv = 0;
+        if (ok) { nv = nedges[cell_id]; ok = !(nv <= 0 || nv > ORC_MAX_VERTEX_NUM); }
+        if (ok) ok = is_in_mesh(&m, cell_id, pos);
+        if (!ok) { set_pixel(img, width, height, ih, jw, NAN, NAN, NAN); continue; }
+        int64_t vidx[ORC_MAX_VERTEX_NUM];
+        double w[ORC_MAX_VERTEX_NUM];
+        cell_weights(&m, cell_id, pos, nv, vidx, w);
+        v3 vel = calc_velocity(vidx, w, nv, L, fixed_layer, vel_v);
+        double zon, mer;
+        xyz_to_enu(pos, vel, &zon, &mer);
+        set_pixel(img, width, height, ih, jw, zon, mer, 0.0);
+    }
+    bins_free(bins);
+    return 0;
+}
+
+/* MPASOField::isOnOcean, src/Core/MPASOField.cpp:36-81: returns is_land */
+static int is_land(const orc_mesh* m, int cell_id, v3 position, int nv)
+{
+    double first = 0.0;
+    for (int k = 0; k < nv; ++k) {
+        int64_t A_idx = (int64_t)m->vertices_on_cell[(int64_t)cell_id * m->max_edges + k] - 1;
+        int64_t B_idx = (int64_t)m->vertices_on_cell[(int64_t)cell_id * m->max_edges + ((k + 1) % nv)] - 1;
+        v3 A = v3_ld(m->vertex_xyz, A_idx), B = v3_ld(m->vertex_xyz, B_idx);
+        v3 O = v3_make(0.0, 0.0, 0.0);
+        v3 AO = v3_sub(O, A), BO = v3_sub(O, B), A_point = v3_sub(position, A);
+        v3 surface_normal = v3_cross(AO, BO);
+        double direction = v3_dot(surface_normal, A_point);
+        double sign = (direction > 0) ? 1.0 : -1.0;
+        if (k == 0) first = sign;
+        else if (sign != first) return 1;
+    }
+    return 0;
+}
+
+int orc_regrid_fixed_latitude(int n_cells, int n_vertices, int max_edges, int L,
+                              const double* cell_xyz, const double* vertex_xyz, const int32_t* voc, const int32_t* coc, const int32_t* nedges,
+                              const double* ztop_v, const double* vel_v, int width, int height, double minLon, double maxLon,
+                              double fixed_lat, double minDepth, double maxDepth, double* img, int32_t* pixel_cell)
+{
+    orc_mesh m = {n_cells, n_vertices, max_edges, L, cell_xyz, vertex_xyz, voc, coc, nedges};
+    const int nVert = L;
+    const double i_step = (height > 1) ? (maxDepth - minDepth) / (height - 1) : 0.0;
+    const double j_step = (width > 1) ? (maxLon - minLon) / (width - 1) : 0.0;
+    orc_bins* bins = bins_build(n_cells, cell_xyz);
+    for (int64_t gid = 0; gid < (int64_t)width * height; ++gid) {
+        const int ih = (int)(gid / width), jw = (int)(gid % width);
+        const double depth_plot = minDepth + ih * i_step;
+        const double DEPTH = -fabs(depth_plot);
+        const double lon = minLon + jw * j_step;
+        /* convertRadianLatLonToXYZ */
+        const double theta = fixed_lat * (M_PI / 180.0), phi = lon * (M_PI / 180.0);
+        const double r = 6371010.0f;
+        double costheta = cos(theta), cosphi = cos(phi), sintheta = sin(theta), sinphi = sin(phi);
+        double pp[3] = {r * costheta * cosphi, r * costheta * sinphi, r * sintheta};
+        v3 position = v3_make(pp[0], pp[1], pp[2]);
+        const int cell_id = bins_nearest(bins, n_cells, cell_xyz, pp);
+        if (pixel_cell) pixel_cell[gid] = cell_id;
+#define ORC_NANPX() do { set_pixel(img, width, height, ih, jw, NAN, NAN, NAN); } while (0)
+        if (cell_id < 0 || cell_id >= n_cells) { ORC_NANPX(); continue; }
+        const int nv = nedges[cell_id];
+        if (nv <= 0 || nv > ORC_MAX_VERTEX_NUM) { ORC_NANPX(); continue; }
+        if (is_land(&m, cell_id, position, nv)) { ORC_NANPX(); continue; }
+        int64_t vidx[ORC_MAX_VERTEX_NUM];
+        double w[ORC_MAX_VERTEX_NUM];
+        cell_weights(&m, cell_id, position, nv, vidx, w);
+        double col[ORC_MAX_VERTICAL_LEVEL_NUM];
+        for (int k = 0; k < nVert; ++k) {
+            double z_acc = 0.0;
+            for (int v = 0; v < nv; ++v) z_acc += w[v] * ztop_v[vidx[v] * L + k];
+            col[k] = z_acc;
+        }
+        for (int k = 1; k < nVert; ++k)
+            if (col[k] > col[k - 1]) col[k] = col[k - 1] - 1e-9;
+        int layer = -1;
+        const double EPSILON = 1e-6;
+        if (DEPTH > col[0] + EPSILON || DEPTH < col[nVert - 1] - EPSILON) { ORC_NANPX(); continue; }
+        for (int k = 1; k < nVert; ++k) {
+            double z_up = col[k - 1], z_dn = col[k];
+            if (z_up < z_dn) { double t = z_up; z_up = z_dn; z_dn = t; }
+            if (DEPTH <= z_up + EPSILON && DEPTH >= z_dn - EPSILON) { layer = k; break; }
+        }
+        if (layer == -1) { ORC_NANPX(); continue; }
+        double dn = col[layer], up = col[layer - 1];
+        if (up < dn) { double t = up; up = dn; dn = t; }
+        const double denom = up - dn;
+        if (fabs(denom) < 1e-30) { ORC_NANPX(); continue; }
+        const double t = (DEPTH - dn) / denom;
+        v3 vel_up = calc_velocity(vidx, w, nv, L, layer - 1, vel_v);
+        v3 vel_dn = calc_velocity(vidx, w, nv, L, layer, vel_v);
+        v3 final_vel = v3_add(v3_mul(vel_dn, (1.0 - t)), v3_mul(vel_up, t));
+        double zon, mer;
+        xyz_to_enu(position, final_vel, &zon, &mer);
+        set_pixel(img, width, height, ih, jw, zon, mer, 0.0);
+#undef ORC_NANPX
+    }
+    bins_free(bins);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------- */
 /* a16: line assembly + NaN trimming, src/Common/TrajectoryCommon.h:43-190                */
 /* ------------------------------------------------------------------------------------- */
 /* raw_pos/raw_vel: [n][each][3] -> lines: points/velocity [n][each+1][3], last [n][3].

@@ -175,6 +175,30 @@ def remap(mesh, prep: Prepared, width, height, lat_range=(-90.0, 90.0), lon_rang
     return {"img0": img0, "img1": img1, "pixel_cell": cells.reshape(height, width)}
 
 
+def remap_fixed_layer(mesh, prep: Prepared, width, height, layer, lat_range=(-90.0, 90.0), lon_range=(-180.0, 180.0)):
+    lib = _load()
+    L = prep.ztop_v.shape[1]
+    img = np.zeros((height, width, 4)); cells = np.zeros(width * height, dtype=np.int32)
+    margs, keep = _mesh_args(mesh, L)
+    rc = lib.orc_remap_fixed_layer(*margs, _p(prep.vel_v), C.c_int(width), C.c_int(height), C.c_double(lat_range[0]),
+                                   C.c_double(lat_range[1]), C.c_double(lon_range[0]), C.c_double(lon_range[1]), C.c_int(int(layer)),
+                                   _p(img), _p(cells))
+    assert rc == 0
+    return {"img": img, "pixel_cell": cells.reshape(height, width)}
+
+
+def regrid_fixed_latitude(mesh, prep: Prepared, width, height, latitude, depth_min, depth_max, lon_range=(-180.0, 180.0)):
+    lib = _load()
+    L = prep.ztop_v.shape[1]
+    img = np.zeros((height, width, 4)); cells = np.zeros(width * height, dtype=np.int32)
+    margs, keep = _mesh_args(mesh, L)
+    rc = lib.orc_regrid_fixed_latitude(*margs, _p(prep.ztop_v), _p(prep.vel_v), C.c_int(width), C.c_int(height),
+                                       C.c_double(lon_range[0]), C.c_double(lon_range[1]), C.c_double(latitude),
+                                       C.c_double(depth_min), C.c_double(depth_max), _p(img), _p(cells))
+    assert rc == 0
+    return {"img": img, "pixel_cell": cells.reshape(height, width)}
+
+
 def pixel_positions(width, height, lat_range=(-90.0, 90.0), lon_range=(-180.0, 180.0)) -> np.ndarray:
     lib = _load()
     out = np.zeros((height, width, 3))

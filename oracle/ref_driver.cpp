@@ -13,6 +13,8 @@
 // (include/api/MOPS.h:20-102, call order of tutorial/streamLine.cpp:72-103).
 #include "api/MOPS.h"
 #include "Core/MPASOVisualizer.h"
+#include "Core/CPUContext.h"
+#include "Core/RuntimeContext.h"
 #include <tbb/parallel_for.h>
 
 #include <cstdint>
@@ -349,6 +351,37 @@ int refo_remap_fixed_depth(int width, int height, double lat_min, double lat_max
     if (img0 && imgs.size() > 0) std::memcpy(img0, imgs[0].mPixels.data(), bytes);
     if (img1 && imgs.size() > 1) std::memcpy(img1, imgs[1].mPixels.data(), bytes);
     return static_cast<int>(imgs.size());
+}
+
+// VisualizeFixedLayer through the reference's facade (src/Core/MPASOVisualizer.cpp:17-20)
+int refo_remap_fixed_layer(int width, int height, double lat_min, double lat_max, double lon_min, double lon_max,
+                           int layer, double* img)
+{
+    VisualizationSettings cfg;
+    cfg.imageSize = vec2(width, height);
+    cfg.LatRange = vec2(lat_min, lat_max);
+    cfg.LonRange = vec2(lon_min, lon_max);
+    cfg.FixedLayer = layer;
+    ImageBuffer<double> im(width, height);
+    CPUContext cpu_ctx;
+    cpu_ctx.backend = CPUBackend::kTBB;
+    MPASOVisualizer::VisualizeFixedLayer(MOPS_GetFieldSnapshots().get(), &cfg, &im, RuntimeContext::FromCPU(cpu_ctx));
+    std::memcpy(img, im.mPixels.data(), static_cast<size_t>(width) * height * 4 * sizeof(double));
+    return 0;
+}
+
+// VisualizeFixedLatitude through MOPSApp::runReGrid (src/Core/MOPSApp.cpp:198-210)
+int refo_regrid_fixed_latitude(int width, int height, double lon_min, double lon_max, double latitude, double* img)
+{
+    VisualizationSettings cfg;
+    cfg.imageSize = vec2(width, height);
+    cfg.LonRange = vec2(lon_min, lon_max);
+    cfg.LatRange = vec2(-90.0, 90.0);
+    cfg.FixedLatitude = latitude;
+    cfg.FixedDepth = 0.0;
+    ImageBuffer<double> im = app.runReGrid(&cfg);
+    std::memcpy(img, im.mPixels.data(), static_cast<size_t>(width) * height * 4 * sizeof(double));
+    return 0;
 }
 
 // Known answers the reference's own unit tests hold for hot-adjacent math

@@ -59,6 +59,8 @@ def _load():
     lib.refo_pathline.restype = C.c_int64
     lib.refo_remap_fixed_depth.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    lib.refo_remap_fixed_layer.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _f64p]
+    lib.refo_regrid_fixed_latitude.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _f64p]
     lib.refo_gauss3.argtypes = [_f64p, _f64p, _f64p]
     lib.refo_wachspress.argtypes = [_f64p, _f64p, C.c_int, _f64p]
     lib.refo_set_threads.argtypes = [C.c_int]
@@ -195,6 +197,17 @@ class RefOracle:
         assert nl == n, (nl, n)
         return {"points": pts, "velocity": vel, "temperature": temp, "salinity": sal, "seeds_out": seeds,
                 "seconds": sec.value}
+
+    def remap_fixed_layer(self, width, height, layer, lat_range=(-90.0, 90.0), lon_range=(-180.0, 180.0)):
+        img = np.zeros((height, width, 4))
+        self.lib.refo_remap_fixed_layer(width, height, lat_range[0], lat_range[1], lon_range[0], lon_range[1], int(layer), img)
+        return img
+
+    def regrid_fixed_latitude(self, width, height, latitude, lon_range=(-180.0, 180.0)):
+        """depth axis = refBottomDepth.front() .. back() of the grid this session was built with"""
+        img = np.zeros((height, width, 4))
+        self.lib.refo_regrid_fixed_latitude(width, height, lon_range[0], lon_range[1], float(latitude), img)
+        return img
 
     def remap(self, width, height, lat_range=(-90.0, 90.0), lon_range=(-180.0, 180.0), depth=800.0):
         img0 = np.zeros((height, width, 4)); img1 = np.zeros((height, width, 4))

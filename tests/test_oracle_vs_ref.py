@@ -91,3 +91,21 @@ def test_remap(session):
         # pixel cells are the reference's own KD-tree answers
         pos = P.pixel_positions(w, h)
         assert _same(o.locate(pos.reshape(-1, 3)).reshape(h, w), b["pixel_cell"])
+
+
+def test_fixed_layer_and_fixed_latitude_views(session):
+    """the two other views, oracle restatement vs the compiled reference, bit for bit"""
+    m, s0, s1, o = session
+    o.activate(0, None)
+    p0 = P.prepare(m, s0)
+    L = s0.n_levels
+    for layer in (0, 3, L - 1, L + 5, -2):
+        r = o.remap_fixed_layer(60, 30, layer)
+        b = P.remap_fixed_layer(m, p0, 60, 30, layer)
+        assert _same(r, b["img"]), layer
+    ref_bottom = np.cumsum(np.full(L, 5000.0 / L))  # what RefOracle hands the grid
+    for lat in (0.0, 37.5, -62.0):
+        r = o.regrid_fixed_latitude(80, 25, lat)
+        b = P.regrid_fixed_latitude(m, p0, 80, 25, lat, ref_bottom[0], ref_bottom[-1])
+        assert _same(r, b["img"]), lat
+        assert np.isfinite(b["img"][..., 0]).any()

@@ -275,3 +275,24 @@ def test_walk_mode_crosses_cells_and_matches_analytic_rotation(eng, P):
     eu = eng.streamline(0, seeds, 600, dur, 86400, depth=100.0, method="euler")
     err_eu = np.linalg.norm(eu["pos"] - rot, axis=1)
     print(f"[walk] rk4-walk max err {err.max():.1f} m, euler max err {err_eu.max():.1f} m over {travelled.max() / 1e3:.0f} km")
+
+
+@pytest.mark.parametrize("variant", ["rich", "nonmono"])
+def test_fixed_layer_and_fixed_latitude_views(eng, P, variant):
+    """VisualizeFixedLayer / VisualizeFixedLatitude on the device vs the oracle"""
+    m, s0, s1 = _setup(eng, 4, 12, variant)
+    prep = P.prepare(m, s0)
+    for layer in (0, 5, 11, 40, -3):
+        got = eng.remap_fixed_layer(0, 72, 36, layer)
+        want = P.remap_fixed_layer(m, prep, 72, 36, layer)
+        assert np.array_equal(got["pixel_cell"], want["pixel_cell"])
+        assert np.array_equal(np.isnan(got["img"]), np.isnan(want["img"]))
+        assert np.allclose(got["img"], want["img"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    for lat in (0.0, 41.0, -70.0):
+        got = eng.regrid_fixed_latitude(0, 90, 30, lat, 416.0, 5000.0)
+        want = P.regrid_fixed_latitude(m, prep, 90, 30, lat, 416.0, 5000.0)
+        assert np.array_equal(got["pixel_cell"], want["pixel_cell"])
+        nan_g, nan_w = np.isnan(got["img"]), np.isnan(want["img"])
+        print(f"[latitude/{variant}/{lat}] nan ref={int(nan_w.sum())} gpu={int(nan_g.sum())}")
+        assert np.array_equal(nan_g, nan_w)
+        assert np.allclose(got["img"], want["img"], rtol=1e-9, atol=1e-12, equal_nan=True)

@@ -39,3 +39,37 @@ def test_pymops_demo_matches_oracle():
     assert len(imgs) == 2 and imgs[0].shape == (180, 360, 4)
     assert np.allclose(imgs[0], ref["img0"], rtol=1e-9, atol=1e-12, equal_nan=True)
     assert np.allclose(imgs[1], ref["img1"], rtol=1e-9, atol=1e-9, equal_nan=True)
+
+
+def test_pymops_regrid_and_fixed_layer():
+    sys.path.insert(0, os.path.join(ROOT, "tutorial"))
+    sys.path.insert(0, os.path.join(ROOT, "tools", "pyMOPS"))
+    import pyMOPS
+    import pyMOPS_demo
+    from mops_b200 import synthetic as S
+    from oracle import port_oracle as P
+    mesh = S.icosahedral_mesh(4)
+    snap = S.solid_body_snapshot(mesh, 12, 1.5, tilt=0.3, shear=0.3, bumpy=0.2)
+    grid = pyMOPS_demo.make_grid(mesh, 12)
+    ref_bottom = np.cumsum(np.full(12, 5000.0 / 12))
+    grid.setRefBottomDepth(ref_bottom)
+    sol = pyMOPS_demo.make_solution(snap, 0)
+    pyMOPS.MOPS_Init("gpu")
+    pyMOPS.MOPS_Begin()
+    pyMOPS.MOPS_AddGridMesh(grid)
+    pyMOPS.MOPS_AddAttribute(77, sol)
+    pyMOPS.MOPS_End()
+    pyMOPS.MOPS_ActiveAttribute(77)
+    prep = P.prepare(mesh, snap)
+    vis = pyMOPS.VisualizationSettings()
+    vis.imageSize = (100, 40)
+    vis.LatRange = (-90.0, 90.0)
+    vis.LonRange = (-180.0, 180.0)
+    vis.FixedLatitude = 25.0
+    img = pyMOPS.MOPS_RunReGrid(vis)
+    want = P.regrid_fixed_latitude(mesh, prep, 100, 40, 25.0, ref_bottom[0], ref_bottom[-1])
+    assert np.allclose(img, want["img"], rtol=1e-9, atol=1e-12, equal_nan=True) and np.isfinite(img[..., 0]).any()
+    vis.FixedLayer = 4
+    img = pyMOPS.MOPS_RunFixedLayer(vis)
+    want = P.remap_fixed_layer(mesh, prep, 100, 40, 4)
+    assert np.allclose(img, want["img"], rtol=1e-9, atol=1e-12, equal_nan=True)

@@ -8,7 +8,6 @@
 // MOPS_RunRemapping (list of (H,W,4) arrays), the timing getters.  Differences: numpy arrays are
 // taken with bulk copies instead of per-element loops, and two additional *Flat entry points return
 // whole (N, M, 3) arrays for large particle counts (a Python list of 64 M dicts is not an option).
-// Not bound (out of the hot path): MOPS_RunReGrid.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -135,6 +134,9 @@ PYBIND11_MODULE(pyMOPS, m)
             if (arr.ndim() != 1) throw std::runtime_error("Input array must be 1D");
             self.setGridAttributesInt(type, std::vector<size_t>(arr.data(), arr.data() + arr.shape(0)));
         })
+        .def("setRefBottomDepth", [](MOPS::MPASOGrid& self, arr_d arr) {
+            self.cellRefBottomDepth_vec.assign(arr.data(), arr.data() + arr.size());
+        })
         .def("setGridAttributesFloat", [](MOPS::MPASOGrid& self, MOPS::GridAttributeType type,
                                           py::array_t<float, py::array::c_style | py::array::forcecast> arr) {
             if (arr.ndim() != 1) throw std::runtime_error("Input array must be 1D");
@@ -187,6 +189,8 @@ PYBIND11_MODULE(pyMOPS, m)
         .def_property("DepthRange", [](const MOPS::VisualizationSettings& s) { return tup(s.DepthRange); },
                       [](MOPS::VisualizationSettings& s, py::tuple t) { s.DepthRange = to_vec2(t, "DepthRange"); })
         .def_readwrite("FixedLatitude", &MOPS::VisualizationSettings::FixedLatitude)
+        .def_property("FixedLayer", [](const MOPS::VisualizationSettings& s) { return s.FixedLayer; },
+                      [](MOPS::VisualizationSettings& s, double v) { s.FixedLayer = v; })
         .def_property("FixedDepth", [](const MOPS::VisualizationSettings& s) { return s.FixedDepth; },
                       [](MOPS::VisualizationSettings& s, double v) { s.FixedDepth = v; })
         .def_readwrite("TimeStep", &MOPS::VisualizationSettings::TimeStep)
@@ -241,6 +245,14 @@ PYBIND11_MODULE(pyMOPS, m)
         return out;
     });
 
+    m.def("MOPS_RunReGrid", [](MOPS::VisualizationSettings* config) {
+        auto img = MOPS::app.runReGrid(config);
+        return py::array_t<double>({img.getHeight(), img.getWidth(), 4}, img.mPixels.data());
+    }, "Run regridding at fixed latitude");
+    m.def("MOPS_RunFixedLayer", [](MOPS::VisualizationSettings* config) {
+        auto img = MOPS::app.runFixedLayer(config);
+        return py::array_t<double>({img.getHeight(), img.getWidth(), 4}, img.mPixels.data());
+    }, "Velocity of one layer (VisualizeFixedLayer)");
     m.def("MOPS_GenerateSeedsPoints", [](MOPS::SamplingSettings* setting) {
         std::vector<CartesianCoord> pts;
         MOPS::MOPS_GenerateSamplePoints(setting, pts);
