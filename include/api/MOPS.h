@@ -113,6 +113,7 @@ public:
     std::vector<double> cellRefBottomDepth_vec;
 
     void initGrid(MPASOReader* reader); // src/Core/MPASOGrid.cpp:190-217 (moves the arrays out of the reader)
+    void initGrid_DemoLoading(const char* yaml_path); // mesh substream of the YAML, as CLI/main.cpp:104 uses it
     void setGridAttribute(GridAttributeType type, int val);
     void setGridAttributesVec3(GridAttributeType type, const std::vector<vec3>& vec);
     void setGridAttributesVec2(GridAttributeType type, const std::vector<vec2>& vec);
@@ -133,6 +134,8 @@ public:
     std::shared_ptr<void> gt; // open record handed over by the reader
 
     void initSolution(MPASOReader* reader); // src/Core/MPASOSolution.cpp:278-320
+    // global record index `timestep` of the data substream (all files, in order), as CLI/main.cpp:111 uses it
+    void initSolution_DemoLoading(const char* yaml_path, int timestep);
     // read one more cell-major variable of the open record into mDoubleAttributes[name]
     // (src/Core/MPASOSolution.cpp:381-411); float variables are widened to double
     void addAttribute(std::string name, AttributeFormat type);

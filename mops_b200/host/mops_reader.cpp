@@ -150,6 +150,37 @@ MPASOReader::Ptr MPASOReader::readSolData(const std::string& yaml_path, const st
     return reader;
 }
 
+void MPASOGrid::initGrid_DemoLoading(const char* yaml_path)
+{
+    auto r = MPASOReader::readGridData(yaml_path);
+    initGrid(r.get());
+}
+
+void MPASOSolution::initSolution_DemoLoading(const char* yaml_path, int timestep)
+{
+    // the global record index is resolved to (file, local record); the file is then addressed by name,
+    // which is what readSolData expects
+    try {
+        io::Stream st;
+        st.parse_yaml(yaml_path);
+        for (auto& sub : st.substreams) {
+            if (sub->is_static) continue;
+            for (size_t i = sub->filenames.size(); i-- > 0;) {
+                if (timestep >= sub->first_timestep_per_file[i]) {
+                    auto r = MPASOReader::readSolData(yaml_path, sub->filenames[i], timestep - sub->first_timestep_per_file[i]);
+                    initSolution(r.get());
+                    mTimesteps = timestep;
+                    return;
+                }
+            }
+        }
+        throw std::runtime_error("no data substream");
+    } catch (const std::exception& e) {
+        std::cerr << "[MPASOSolution]::initSolution_DemoLoading: " << e.what() << std::endl;
+        std::exit(-1);
+    }
+}
+
 void MPASOGrid::initGrid(MPASOReader* r)
 {
     mCellsSize = r->mCellsSize; mEdgesSize = r->mEdgesSize; mMaxEdgesSize = r->mMaxEdgesSize; mVertexSize = r->mVertexSize;

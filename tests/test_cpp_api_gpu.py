@@ -133,3 +133,41 @@ def test_remapping_tutorial_config_c2_small(built, tmp_path):
     assert np.allclose(imgs[0], ref["img0"], rtol=1e-9, atol=1e-12, equal_nan=True)
     assert np.allclose(imgs[1], ref["img1"], rtol=1e-9, atol=1e-9, equal_nan=True)
     assert abs(imgs[0][90, 180, 2] - 30.0 * np.cos(0.3)) < 0.5  # speed at (lat 0, lon 0): axis tilted 0.3 rad towards +x
+
+
+def test_cli_on_mpas_files(built, tmp_path):
+    """the reference CLI's flow (-i yaml -t timestep -g days -d depth): remap + 31x31-seed Euler streamline
+    dumped as TXT; both checked against the oracle"""
+    from oracle import port_oracle as P
+    m = cases.mesh(5)
+    snaps = [S.solid_body_snapshot(m, 20, 0.6 + 0.2 * i, tilt=0.3, shear=0.2, with_attrs=True) for i in range(2)]
+    for s in snaps:
+        s.attrs = {k: v.astype(np.float32).astype(np.float64) for k, v in s.attrs.items()}
+    yaml = S.write_mpas_files(str(tmp_path / "nc"), m, snaps)
+    out = tmp_path / "out"
+    out.mkdir()
+    subprocess.check_call([os.path.join(built, "mops_cli"), "-i", yaml, "-t", "1", "-g", "2", "-d", "120", "--imagesize", "180x90",
+                           "--out", str(out)])
+    prep = P.prepare(m, snaps[1])
+    # remap
+    with open(out / "remap_t1.bin", "rb") as f:
+        n, w, h = np.fromfile(f, dtype=np.int32, count=3)
+        imgs = np.fromfile(f, dtype=np.float64).reshape(n, h, w, 4)
+    ref = P.remap(m, prep, 180, 90, depth=120.0)
+    assert n == 2 and np.allclose(imgs[0], ref["img0"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert (out / "output_0_ch2.png").read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
+    # streamline TXT: reference format, Euler (API default), dt 1 h, 2 days, record 6 h
+    seeds = S.seed_grid(31, 31, (35.0, 45.0), (-90.0, -15.0))
+    cells = P.locate(m, seeds)
+    b = P.streamline(m, prep, seeds, cells, 3600, 2 * 86400, 6 * 3600, depth=120.0, method="euler")
+    f = P.finalize_lines(seeds, b["raw_pos"], b["raw_vel"])
+    txt = (out / "traj_line_1.txt").read_text().splitlines()
+    assert txt[0] == "Line_Index Point_Index Position_X Position_Y Position_Z Velocity_X Velocity_Y Velocity_Z"
+    rows = np.array([[float(x) for x in ln.split()] for ln in txt[1:]])
+    per = f["points"].shape[1]
+    assert rows.shape == (seeds.shape[0] * per, 8)
+    assert np.array_equal(rows[:, 0], np.repeat(np.arange(seeds.shape[0]), per))
+    assert np.allclose(rows[:, 2:5], f["points"].reshape(-1, 3), rtol=1e-5)       # default ostream precision: 6 digits
+    assert np.allclose(rows[:, 5:8], f["velocity"].reshape(-1, 3), rtol=1e-5, atol=1e-12)
+    vtk = (out / "traj_line_1.vtk").read_text()
+    assert vtk.startswith("# vtk DataFile Version 3.0") and f"LINES {seeds.shape[0]} " in vtk

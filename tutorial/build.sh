@@ -13,4 +13,6 @@ for t in streamLine pathLine reMapping; do
     $CXX -std=c++17 -O2 -I"$ROOT/include" -I"$HERE" -o "$HERE/bin/$t" "$HERE/$t.cpp" \
         -L"$ROOT/mops_b200" -lmops_api -lmops_b200 -Wl,-rpath,"$ROOT/mops_b200" -Wl,-rpath,"$CUDA_LIB"
 done
-echo "built $ROOT/mops_b200/libmops_api.so and $HERE/bin/{streamLine,pathLine,reMapping}"
+$CXX -std=c++17 -O2 -I"$ROOT/include" -I"$ROOT/mops_b200/host" -o "$HERE/bin/mops_cli" "$ROOT/CLI/main.cpp" \
+    -L"$ROOT/mops_b200" -lmops_api -lmops_b200 -Wl,-rpath,"$ROOT/mops_b200" -Wl,-rpath,"$CUDA_LIB"
+echo "built $ROOT/mops_b200/libmops_api.so and $HERE/bin/{streamLine,pathLine,reMapping,mops_cli}"
