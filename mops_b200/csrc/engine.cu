@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -467,13 +468,33 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     int *d_log = nullptr, *d_status = nullptr, *d_steps = nullptr, *d_fcell = nullptr;
     double* d_edge = nullptr;
     const int* d_cell0_ext = nullptr;
+    // HOST mode: outputs are staged in device scratch and copied back with cudaMemcpyAsync.  Opt-in
+    // experiment (MOPS_ZERO_COPY=1, pinned UVA-mapped buffers): the kernel writes its records straight into
+    // host memory over PCIe.  Measured on B200 it is a loss -- 24-byte scattered stores become tiny PCIe
+    // writes: 8.3 s per bench step instead of 3.4 s staged -- so it is off by default.
+    auto mapped = [](void* p) -> void* {
+        if (!p) return nullptr;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return (a.type == cudaMemoryTypeHost && a.devicePointer) ? a.devicePointer : nullptr;
+    };
+    bool zero_copy_out = false;
     if (host) {
         if ((rc = ensure(ctx, ctx->p_xyz, (size_t)n * 24))) return rc;
         if ((rc = ensure(ctx, ctx->p_depth, (size_t)n * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->p_out_pos, out_bytes))) return rc;
-        if ((rc = ensure(ctx, ctx->p_out_vel, out_bytes))) return rc;
         d_xyz = (double*)ctx->p_xyz.p; d_depth = (float*)ctx->p_depth.p;
-        d_out_pos = (double*)ctx->p_out_pos.p; d_out_vel = (double*)ctx->p_out_vel.p;
+        void* mp = mapped(io->out_pos);
+        void* mv = mapped(io->out_vel);
+        void* ma = want_attr ? mapped(io->out_attr) : nullptr;
+        zero_copy_out = mp && mv && (!want_attr || ma) && getenv("MOPS_ZERO_COPY") != nullptr;
+        if (zero_copy_out) {
+            d_out_pos = (double*)mp; d_out_vel = (double*)mv;
+            if (want_attr) d_out_attr = (double*)ma;
+        } else {
+            if ((rc = ensure(ctx, ctx->p_out_pos, out_bytes))) return rc;
+            if ((rc = ensure(ctx, ctx->p_out_vel, out_bytes))) return rc;
+            d_out_pos = (double*)ctx->p_out_pos.p; d_out_vel = (double*)ctx->p_out_vel.p;
+        }
         CK(cudaMemcpyAsync(d_xyz, io->xyz, (size_t)n * 24, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_depth, io->depth, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         if (io->cell0) {
@@ -481,7 +502,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
             CK(cudaMemcpyAsync(ctx->p_cell0.p, io->cell0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
             d_cell0_ext = (const int*)ctx->p_cell0.p;
         }
-        if (want_attr) { if ((rc = ensure(ctx, ctx->p_out_attr, out_bytes))) return rc; d_out_attr = (double*)ctx->p_out_attr.p; }
+        if (want_attr && !zero_copy_out) { if ((rc = ensure(ctx, ctx->p_out_attr, out_bytes))) return rc; d_out_attr = (double*)ctx->p_out_attr.p; }
         if (io->out_cell_log) { if ((rc = ensure(ctx, ctx->p_log, (size_t)n * times * 4))) return rc; d_log = (int*)ctx->p_log.p; }
         if (io->out_status) { if ((rc = ensure(ctx, ctx->p_status, (size_t)n * 4))) return rc; d_status = (int*)ctx->p_status.p; }
         if (io->out_steps) { if ((rc = ensure(ctx, ctx->p_steps, (size_t)n * 4))) return rc; d_steps = (int*)ctx->p_steps.p; }
@@ -494,10 +515,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
         d_edge = io->out_min_edge;
         d_cell0_ext = io->cell0;
     }
-    // the reference's output buffers are value-initialised (TrajectoryCommon.h:20-25)
-    CK(cudaMemsetAsync(d_out_pos, 0, out_bytes, st));
-    CK(cudaMemsetAsync(d_out_vel, 0, out_bytes, st));
-    if (d_out_attr) CK(cudaMemsetAsync(d_out_attr, 0, out_bytes, st));
+    // (the kernel writes every output slot itself, zeros included -- see k_advect)
     if (d_log) CK(cudaMemsetAsync(d_log, 0xff, (size_t)n * times * 4, st));
 
     // start cells in internal numbering
@@ -568,9 +586,11 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     if (host) {
         CK(cudaMemcpyAsync(io->xyz, d_xyz, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(io->depth, d_depth, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(io->out_pos, d_out_pos, out_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(io->out_vel, d_out_vel, out_bytes, cudaMemcpyDeviceToHost, st));
-        if (d_out_attr) CK(cudaMemcpyAsync(io->out_attr, d_out_attr, out_bytes, cudaMemcpyDeviceToHost, st));
+        if (!zero_copy_out) {
+            CK(cudaMemcpyAsync(io->out_pos, d_out_pos, out_bytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(io->out_vel, d_out_vel, out_bytes, cudaMemcpyDeviceToHost, st));
+            if (d_out_attr) CK(cudaMemcpyAsync(io->out_attr, d_out_attr, out_bytes, cudaMemcpyDeviceToHost, st));
+        }
         if (d_log) CK(cudaMemcpyAsync(io->out_cell_log, d_log, (size_t)n * times * 4, cudaMemcpyDeviceToHost, st));
         if (d_status) CK(cudaMemcpyAsync(io->out_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (d_steps) CK(cudaMemcpyAsync(io->out_steps, d_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

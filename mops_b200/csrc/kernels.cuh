@@ -376,10 +376,16 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
         bool first_vel = true;
         double edge_min = 1.0e300;
 
+        // Every output slot is written exactly once by this thread (no host-side memset of the buffers,
+        // which may be pinned host memory written over PCIe): the reference's buffers are
+        // value-initialised (TrajectoryCommon.h:20-25), so slots it never reaches hold (0,0,0).
+        const bool has_attr_out = PATH && P.attr_count > 0 && P.out_attr;
         if (cell < 0 || cell >= P.nC) {
             status = ST_BAD_CELL; // VK:895-897: nothing is written, not even the seed
         } else {
             st3(P.out_pos, base, pos.x, pos.y, pos.z); // VK:901
+            st3(P.out_vel, base, 0.0, 0.0, 0.0);       // overwritten by the first completed step (VK:988-991)
+            if (P.out_attr) st3(P.out_attr, base, 0.0, 0.0, 0.0);
             for (int step = 0; step < P.times; ++step) {
                 run_time += abs(P.delta_t);
                 if (step > 0) {
@@ -508,6 +514,15 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                 }
             }
         }
+        {
+            int k0 = (status == ST_BAD_CELL) ? 0 : ((upd < 1) ? 1 : ((upd < P.each) ? upd : P.each));
+            for (int k = k0; k < P.each; ++k) {
+                st3(P.out_pos, base + k, 0.0, 0.0, 0.0);
+                st3(P.out_vel, base + k, 0.0, 0.0, 0.0);
+                if (P.out_attr) st3(P.out_attr, base + k, 0.0, 0.0, 0.0);
+            }
+        }
+        (void)has_attr_out;
         P.pos[3 * pid] = pos.x; P.pos[3 * pid + 1] = pos.y; P.pos[3 * pid + 2] = pos.z;
         P.depth[pid] = depth_f;
         if (P.status) P.status[pid] = status;

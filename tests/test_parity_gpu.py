@@ -296,3 +296,42 @@ def test_fixed_layer_and_fixed_latitude_views(eng, P, variant):
         print(f"[latitude/{variant}/{lat}] nan ref={int(nan_w.sum())} gpu={int(nan_g.sum())}")
         assert np.array_equal(nan_g, nan_w)
         assert np.allclose(got["img"], want["img"], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("zero_copy", [False, True])
+def test_pinned_host_outputs(eng, P, zero_copy, monkeypatch):
+    """HOST-mode call with pinned output buffers, staged (default) and with the opt-in zero-copy path
+    (MOPS_ZERO_COPY=1: the kernel writes the records straight into host memory).  Every slot is written by
+    the kernel itself (no memset): results identical to the pageable path, stopped particles leave zeros."""
+    import ctypes as C
+    import os
+    import torch
+    from mops_b200 import capi
+    if zero_copy:
+        monkeypatch.setenv("MOPS_ZERO_COPY", "1")
+    else:
+        monkeypatch.delenv("MOPS_ZERO_COPY", raising=False)
+    m, s0, s1 = _setup(eng, 4, 12, "rich")
+    seeds = cases.seeds_random(6000, seed=41)
+    n, dur, rec = seeds.shape[0], 43200, 3600
+    each = dur // rec
+    staged = eng.pathline(0, 1, seeds, DT, dur, rec, depth=600.0, method="rk4")   # pageable numpy buffers
+    assert (staged["status"] != 0).sum() > 100
+
+    def pinned(shape, dtype):
+        return torch.zeros(shape, dtype=dtype).pin_memory()
+    xyz = pinned((n, 3), torch.float64); xyz.copy_(torch.from_numpy(seeds))
+    depth = pinned((n,), torch.float32); depth.fill_(600.0)
+    out_pos = pinned((n, each, 3), torch.float64); out_pos.fill_(7.0)   # garbage the kernel must overwrite
+    out_vel = pinned((n, each, 3), torch.float64); out_vel.fill_(7.0)
+    out_attr = pinned((n, each, 3), torch.float64); out_attr.fill_(7.0)
+    status = pinned((n,), torch.int32)
+    cfg = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, dur, rec, capi.MEM_HOST, 1)
+    io = capi.TrajIO(n, xyz.data_ptr(), depth.data_ptr(), None, out_pos.data_ptr(), out_vel.data_ptr(), out_attr.data_ptr(),
+                     None, status.data_ptr(), None, None)
+    st = eng.traj_device(True, (0, 1), cfg, io, want_stats=True)
+    assert np.array_equal(out_pos.numpy(), staged["raw_pos"])
+    assert np.array_equal(out_vel.numpy(), staged["raw_vel"])
+    assert np.array_equal(out_attr.numpy(), staged["raw_attr"])
+    assert np.array_equal(status.numpy(), staged["status"]) and np.array_equal(xyz.numpy(), staged["pos"])
+    assert int(st.particle_steps) == int(staged["steps_alive"].sum())
