@@ -361,3 +361,65 @@ def write_mpas_files(directory: str, mesh: Mesh, snaps, dates=None, per_file: in
     with open(path, "w") as fh:
         fh.write(yaml)
     return path
+
+
+def voronoi_mesh(points_unit: np.ndarray, radius: float = SPHERE_RADIUS) -> Mesh:
+    """MPAS-format arrays of the spherical Voronoi diagram of arbitrary generators (scipy's
+    SphericalVoronoi): cells with anywhere from 3 to 10+ edges, so maxEdges > 6 and the engine's wider cell
+    records (M = 8, M = 20) are exercised.  Same conventions as icosahedral_mesh (CCW vertices, neighbour k
+    across the edge (vertex k, vertex k+1), 1-based, 0-padded)."""
+    from scipy.spatial import SphericalVoronoi
+    pts = np.asarray(points_unit, dtype=np.float64)
+    pts = pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    sv = SphericalVoronoi(pts, radius=1.0, center=np.zeros(3))
+    sv.sort_vertices_of_regions()
+    n_cells, n_vert = pts.shape[0], sv.vertices.shape[0]
+    counts = np.array([len(r) for r in sv.regions], dtype=np.int32)
+    max_edges = int(counts.max())
+    voc = np.zeros((n_cells, max_edges), dtype=np.int32)
+    coc = np.zeros((n_cells, max_edges), dtype=np.int32)
+    edge_cells = {}
+    regions = []
+    for c, reg in enumerate(sv.regions):
+        reg = list(reg)
+        v = sv.vertices[reg]
+        # make the order counter-clockwise seen from outside
+        if np.dot(np.cross(v[0], v[1]), pts[c]) < 0:
+            reg = reg[::-1]
+        regions.append(reg)
+        for k in range(len(reg)):
+            e = (min(reg[k], reg[(k + 1) % len(reg)]), max(reg[k], reg[(k + 1) % len(reg)]))
+            edge_cells.setdefault(e, []).append(c)
+    for c, reg in enumerate(regions):
+        voc[c, :len(reg)] = np.array(reg) + 1
+        for k in range(len(reg)):
+            e = (min(reg[k], reg[(k + 1) % len(reg)]), max(reg[k], reg[(k + 1) % len(reg)]))
+            other = [x for x in edge_cells[e] if x != c]
+            coc[c, k] = (other[0] + 1) if other else 0
+    # cellsOnVertex: the three generators of the Delaunay triangle whose circumcentre the vertex is
+    cov = np.zeros((n_vert, 3), dtype=np.int32)
+    vcells = [[] for _ in range(n_vert)]
+    for c, reg in enumerate(regions):
+        for vtx in reg:
+            vcells[vtx].append(c)
+    for i, lst in enumerate(vcells):
+        lst = (lst + lst[:1] * 3)[:3] if lst else [0, 0, 0]
+        cov[i] = np.array(lst[:3]) + 1
+    return Mesh(n_cells=n_cells, n_vertices=n_vert, max_edges=max_edges, cell_xyz=np.ascontiguousarray(pts * radius),
+                vertex_xyz=np.ascontiguousarray(sv.vertices * radius), vertices_on_cell=voc, cells_on_cell=coc,
+                cells_on_vertex=cov, n_edges_on_cell=counts, level=-1)
+
+
+def jittered_icosahedral_points(level: int, jitter: float, seed: int) -> np.ndarray:
+    """generators of the icosahedral mesh moved by up to `jitter` x the cell spacing: Voronoi cells with 5..8 edges"""
+    m = icosahedral_mesh(level, radius=1.0)
+    rng = np.random.default_rng(seed)
+    spacing = np.sqrt(4.0 * np.pi / m.n_cells)
+    p = m.cell_xyz + rng.normal(scale=jitter * spacing, size=m.cell_xyz.shape)
+    return p / np.linalg.norm(p, axis=1, keepdims=True)
+
+
+def random_sphere_points(n: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    p = rng.normal(size=(n, 3))
+    return p / np.linalg.norm(p, axis=1, keepdims=True)

@@ -44,3 +44,20 @@ def seeds_grid(n_side=15):
 
 def seeds_random(n, seed=11):
     return S.uniform_sphere_seeds(n, seed, lat_max=85.0)
+
+
+@functools.lru_cache(maxsize=None)
+def voronoi_mesh(kind: str):
+    """general spherical-Voronoi fixtures: 'm8' (jittered icosahedral, 4..8 edges -> 8-wide cell records),
+    'm20' (random generators, up to ~12 edges -> 20-wide records)"""
+    if kind == "m8":
+        return S.voronoi_mesh(S.jittered_icosahedral_points(4, 0.15, 1))
+    if kind == "m20":
+        return S.voronoi_mesh(S.random_sphere_points(1500, 2))
+    raise ValueError(kind)
+
+
+def voronoi_snapshots(kind: str, n_levels: int):
+    m = voronoi_mesh(kind)
+    return (S.solid_body_snapshot(m, n_levels, 2.0, tilt=0.3, shear=0.4, bumpy=0.3, w_amp=2e-3, with_attrs=True),
+            S.solid_body_snapshot(m, n_levels, 3.0, tilt=0.35, shear=0.2, bumpy=0.25, w_amp=-1e-3, with_attrs=True))

@@ -109,3 +109,33 @@ def test_fixed_layer_and_fixed_latitude_views(session):
         b = P.regrid_fixed_latitude(m, p0, 80, 25, lat, ref_bottom[0], ref_bottom[-1])
         assert _same(r, b["img"]), lat
         assert np.isfinite(b["img"][..., 0]).any()
+
+
+@pytest.mark.parametrize("kind", ["m8", "m20"])
+def test_general_voronoi_meshes(kind):
+    """meshes with more than 6 edges per cell (maxEdges 8 / 12): restatement vs compiled reference"""
+    m = cases.voronoi_mesh(kind)
+    s0, s1 = cases.voronoi_snapshots(kind, 9)
+    o = R.RefOracle(m, [s0, s1])
+    try:
+        p0, p1 = P.prepare(m, s0), P.prepare(m, s1)
+        r = o.prepared(0)
+        assert _same(p0.ztop_v, r["ztop_vertex"]) and _same(p0.vel_v, r["vel_vertex"]) and _same(p0.w_v, r["vertvel_vertex"])
+        seeds = cases.seeds_random(600, seed=8)
+        cells = o.locate(seeds)
+        assert _same(P.locate(m, seeds), cells)
+        for method in ("rk4", "euler"):
+            rr = o.streamline(seeds, 600, 86400, 3600, depth=400.0, method=method)
+            b = P.streamline(m, p0, seeds, cells, 600, 86400, 3600, depth=400.0, method=method)
+            f = P.finalize_lines(seeds, b["raw_pos"], b["raw_vel"])
+            assert _same(rr["points"], f["points"]) and _same(rr["velocity"], f["velocity"])
+        o.activate(0, 1)
+        rr = o.pathline(seeds, 600, 86400, 3600, depth=400.0, method="rk4")
+        b = P.pathline(m, p0, p1, seeds, cells, 600, 86400, 3600, depth=400.0, method="rk4")
+        f = P.finalize_lines(seeds, b["raw_pos"], b["raw_vel"], pathline_mode=True)
+        assert _same(rr["points"], f["points"]) and _same(rr["velocity"], f["velocity"])
+        o.activate(0, None)
+        ri, bi = o.remap(64, 32, depth=400.0), P.remap(m, p0, 64, 32, depth=400.0)
+        assert _same(ri["img0"], bi["img0"]) and _same(ri["img1"], bi["img1"])
+    finally:
+        o.close()

@@ -335,3 +335,39 @@ def test_pinned_host_outputs(eng, P, zero_copy, monkeypatch):
     assert np.array_equal(out_attr.numpy(), staged["raw_attr"])
     assert np.array_equal(status.numpy(), staged["status"]) and np.array_equal(xyz.numpy(), staged["pos"])
     assert int(st.particle_steps) == int(staged["steps_alive"].sum())
+
+
+@pytest.mark.parametrize("kind,width", [("m8", 8), ("m20", 20)])
+def test_general_voronoi_meshes_wide_records(eng, P, kind, width):
+    """cells with up to 8 / 12 edges: the 8- and 20-wide cell-record instantiations of every kernel"""
+    m = cases.voronoi_mesh(kind)
+    s0, s1 = cases.voronoi_snapshots(kind, 9)
+    eng.set_mesh(m)
+    eng.set_snapshot(0, s0)
+    eng.set_snapshot(1, s1)
+    assert eng.info().record_width == width
+    p0, p1 = P.prepare(m, s0), P.prepare(m, s1)
+    got = eng.get_prepared(0, attrs=2)
+    assert np.array_equal(got["ztop_vertex"], p0.ztop_v) and np.array_equal(got["vel_vertex"], p0.vel_v)
+    seeds = np.concatenate([cases.seeds_random(3000, seed=8), m.cell_xyz[:100] * 0.9999])
+    cells = P.locate(m, seeds)
+    assert np.array_equal(eng.locate(seeds), cells)
+    for method in ("rk4", "euler"):
+        want = P.streamline(m, p0, seeds, cells, 600, 86400, 3600, depth=400.0, method=method)
+        g = eng.streamline(0, seeds, 600, 86400, 3600, depth=400.0, cell0=cells, method=method, log_cells=True)
+        assert np.array_equal(g["cell_log"], want["cell_log"]) and np.array_equal(g["status"], want["status"])
+        assert np.linalg.norm(g["raw_pos"] - want["raw_pos"], axis=2).max() < 1e-6
+        print(f"[{kind}/{method}] bit-identical={np.array_equal(g['raw_pos'], want['raw_pos'])} stopped={(want['status'] != 0).sum()}")
+    want = P.pathline(m, p0, p1, seeds, cells, 600, 86400, 3600, depth=400.0, method="rk4")
+    g = eng.pathline(0, 1, seeds, 600, 86400, 3600, depth=400.0, cell0=cells, method="rk4", log_cells=True)
+    assert np.array_equal(g["cell_log"], want["cell_log"]) and np.array_equal(g["status"], want["status"])
+    assert np.linalg.norm(g["raw_pos"] - want["raw_pos"], axis=2).max() < 1e-6
+    assert np.allclose(g["raw_attr"], want["raw_attr"], rtol=1e-9, atol=1e-12)
+    wi = P.remap(m, p0, 96, 48, depth=400.0)
+    gi = eng.remap(0, 96, 48, depth=400.0)
+    assert np.array_equal(gi["pixel_cell"], wi["pixel_cell"])
+    assert np.allclose(gi["img0"], wi["img0"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.allclose(gi["img1"], wi["img1"], rtol=1e-9, atol=1e-9, equal_nan=True)
+    wl = P.regrid_fixed_latitude(m, p0, 60, 20, 10.0, 500.0, 4000.0)
+    gl = eng.regrid_fixed_latitude(0, 60, 20, 10.0, 500.0, 4000.0)
+    assert np.allclose(gl["img"], wl["img"], rtol=1e-9, atol=1e-12, equal_nan=True)
