@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--level", type=int, default=9, help="icosahedral bisection level (9 = 2,621,442 cells)")
     ap.add_argument("--layers", type=int, default=80)
+    ap.add_argument("--sweep-host-chunk", type=str, default="", help="experiment: comma list of HOST-mode chunk sizes to time")
     ap.add_argument("--particles", type=int, default=64_000_000, help="TOTAL seeds over all GPUs (strong scaling)")
     ap.add_argument("--interval-steps", type=int, default=120, help="RK4 steps per snapshot interval (720 = 1 day)")
     ap.add_argument("--cpu-level", type=int, default=7)
@@ -376,6 +377,22 @@ def main():
             ps_all = float(ps)
         e2e = {"value": ps_all / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_e / K}
+
+        if args.sweep_host_chunk:  # experiment: HOST-mode pipeline chunk size (particles; 0 = single pass)
+            for c in [int(x) for x in args.sweep_host_chunk.split(",")]:
+                os.environ["MOPS_HOST_CHUNK"] = str(c if c > 0 else 1 << 40)
+                e2e_step(step_no); step_no += 1
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                kk = 0.0
+                for _ in range(2):
+                    st = e2e_step(step_no); step_no += 1
+                    kk += st.kernel_ms
+                torch.cuda.synchronize()
+                if rank == 0:
+                    print(f"[sweep] host_chunk={c} ms_per_step={(time.perf_counter() - t0) * 500:.1f} kernel_ms={kk / 2:.1f}",
+                          file=sys.stderr, flush=True)
+            os.environ.pop("MOPS_HOST_CHUNK", None)
 
     # ---- roofline of the dominant kernel (k_advect<6,true>) ----------------------------------
     peak, peak_src = load_peaks()

@@ -76,6 +76,14 @@ struct mops_ctx {
     Buf s_keys, s_vals, s_keys2, s_vals2, s_tmp;
     Buf r_img0, r_img1, r_cells;
     unsigned long long* counters = nullptr; // [4]
+    // HOST-mode pipeline (large n): two sets of chunk-sized scratch so that the H2D of chunk k+1 and the D2H
+    // of chunk k-1 overlap the kernel of chunk k
+    struct PipeSet {
+        Buf xyz, depth, cell0, cell_int, vals, vals2, keys2, tmp, out_pos, out_vel, out_attr, log, status, steps, fcell, edge;
+        cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    } pipe[2];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> chunk_ev; // (kernel start, kernel end) pairs, grown on demand
 };
 
 namespace {
@@ -422,6 +430,154 @@ void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
     }
 }
 
+
+// one particle range on the device: start cells (given or located) -> Morton order -> advection kernel, all on
+// ctx->stream.  `S` supplies the sort scratch; P carries the device pointers of the range.
+int run_range(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, long long m, const int* d_cell0_ext, int* d_cell_int, Buf& vals,
+              Buf& vals2, Buf& keys2, Buf& tmp, AdvectParams& P, cudaEvent_t ev_loc0, cudaEvent_t ev_loc1, cudaEvent_t ev_k0,
+              cudaEvent_t ev_k1)
+{
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (ev_loc0) CK(cudaEventRecord(ev_loc0, st));
+    if (d_cell0_ext) {
+        k_map_ids<<<blocks_for(m, 256), 256, 0, st>>>(d_cell0_ext, d_cell_int, ctx->c_ext2int, ctx->nC, m);
+        ctx->launches++;
+    } else {
+        dispatch_locate(ctx, m, P.pos, d_cell_int, nullptr);
+    }
+    if (ev_loc1) CK(cudaEventRecord(ev_loc1, st));
+    const int* d_order = nullptr;
+    if (cfg->sort_particles && m > 1) { // processing order: particles sorted by (Morton-numbered) start cell
+        if ((rc = ensure(ctx, vals, (size_t)m * 4))) return rc;
+        if ((rc = ensure(ctx, keys2, (size_t)m * 4))) return rc;
+        if ((rc = ensure(ctx, vals2, (size_t)m * 4))) return rc;
+        k_iota<<<blocks_for(m, 256), 256, 0, st>>>((int*)vals.p, m);
+        ctx->launches++;
+        size_t tmp_bytes = 0;
+        // keys are cell ids in [-1, nC): -1 (invalid) sorts last as unsigned
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned*)d_cell_int, (unsigned*)keys2.p, (const int*)vals.p,
+                                        (int*)vals2.p, (int)m, 0, 32, st);
+        if ((rc = ensure(ctx, tmp, tmp_bytes))) return rc;
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, (const unsigned*)d_cell_int, (unsigned*)keys2.p, (const int*)vals.p,
+                                           (int*)vals2.p, (int)m, 0, 32, st));
+        d_order = (const int*)vals2.p;
+    }
+    P.n = m; P.order = d_order; P.cell0 = d_cell_int;
+    if (ev_k0) CK(cudaEventRecord(ev_k0, st));
+    switch (ctx->M) {
+    case 6: launch_advect<6>(ctx, P, path); break;
+    case 8: launch_advect<8>(ctx, P, path); break;
+    default: launch_advect<20>(ctx, P, path); break;
+    }
+    CK(cudaGetLastError());
+    if (ev_k1) CK(cudaEventRecord(ev_k1, st));
+    return MOPS_OK;
+}
+
+// HOST-mode call on many particles: caller-order chunks are software-pipelined over three streams -- H2D of
+// chunk k+1 and D2H of chunk k-1 overlap the kernel of chunk k (also with pageable buffers, because the
+// blocking D2H of chunk k-1 is issued after the kernel of chunk k has been enqueued).
+int trajectory_host_pipelined(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, const mops_traj_io* io, mops_traj_stats* stats,
+                              AdvectParams P0, int each, int times, bool want_attr, long long chunk, long long launches0)
+{
+    const long long n = io->n;
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    cudaStream_t st = ctx->stream;
+    int rc;
+    while ((int)ctx->chunk_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->chunk_ev.push_back(e);
+    }
+    for (auto& S : ctx->pipe) {
+        if ((rc = ensure(ctx, S.xyz, (size_t)chunk * 24))) return rc;
+        if ((rc = ensure(ctx, S.depth, (size_t)chunk * 4))) return rc;
+        if ((rc = ensure(ctx, S.cell_int, (size_t)chunk * 4))) return rc;
+        if (io->cell0 && (rc = ensure(ctx, S.cell0, (size_t)chunk * 4))) return rc;
+        if ((rc = ensure(ctx, S.out_pos, (size_t)chunk * each * 24))) return rc;
+        if ((rc = ensure(ctx, S.out_vel, (size_t)chunk * each * 24))) return rc;
+        if (want_attr && (rc = ensure(ctx, S.out_attr, (size_t)chunk * each * 24))) return rc;
+        if (io->out_cell_log && (rc = ensure(ctx, S.log, (size_t)chunk * times * 4))) return rc;
+        if (io->out_status && (rc = ensure(ctx, S.status, (size_t)chunk * 4))) return rc;
+        if (io->out_steps && (rc = ensure(ctx, S.steps, (size_t)chunk * 4))) return rc;
+        if (io->out_cell && (rc = ensure(ctx, S.fcell, (size_t)chunk * 4))) return rc;
+        if (io->out_min_edge && (rc = ensure(ctx, S.edge, (size_t)chunk * 8))) return rc;
+    }
+    CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
+    // the copy streams start after everything already queued on the compute stream
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev1, 0));
+    CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev1, 0));
+
+    auto copy_out = [&](int k) -> int {
+        auto& S = ctx->pipe[k & 1];
+        const long long lo = (long long)k * chunk, m = std::min(chunk, n - lo);
+        cudaStream_t so = ctx->copy_out;
+        CK(cudaStreamWaitEvent(so, S.k_done, 0));
+        CK(cudaMemcpyAsync(io->xyz + 3 * lo, S.xyz.p, (size_t)m * 24, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(io->depth + lo, S.depth.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(io->out_pos + lo * each * 3, S.out_pos.p, (size_t)m * each * 24, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(io->out_vel + lo * each * 3, S.out_vel.p, (size_t)m * each * 24, cudaMemcpyDeviceToHost, so));
+        if (want_attr) CK(cudaMemcpyAsync(io->out_attr + lo * each * 3, S.out_attr.p, (size_t)m * each * 24, cudaMemcpyDeviceToHost, so));
+        if (io->out_cell_log) CK(cudaMemcpyAsync(io->out_cell_log + lo * times, S.log.p, (size_t)m * times * 4, cudaMemcpyDeviceToHost, so));
+        if (io->out_status) CK(cudaMemcpyAsync(io->out_status + lo, S.status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        if (io->out_steps) CK(cudaMemcpyAsync(io->out_steps + lo, S.steps.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        if (io->out_cell) CK(cudaMemcpyAsync(io->out_cell + lo, S.fcell.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        if (io->out_min_edge) CK(cudaMemcpyAsync(io->out_min_edge + lo, S.edge.p, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
+        CK(cudaEventRecord(S.out_done, so));
+        return MOPS_OK;
+    };
+
+    for (int k = 0; k < nchunks; ++k) {
+        auto& S = ctx->pipe[k & 1];
+        const long long lo = (long long)k * chunk, m = std::min(chunk, n - lo);
+        cudaStream_t si = ctx->copy_in;
+        if (k >= 2) CK(cudaStreamWaitEvent(si, S.out_done, 0)); // set free again: chunk k-2 has been copied out
+        CK(cudaMemcpyAsync(S.xyz.p, io->xyz + 3 * lo, (size_t)m * 24, cudaMemcpyHostToDevice, si));
+        CK(cudaMemcpyAsync(S.depth.p, io->depth + lo, (size_t)m * 4, cudaMemcpyHostToDevice, si));
+        if (io->cell0) CK(cudaMemcpyAsync(S.cell0.p, io->cell0 + lo, (size_t)m * 4, cudaMemcpyHostToDevice, si));
+        CK(cudaEventRecord(S.in_done, si));
+
+        CK(cudaStreamWaitEvent(st, S.in_done, 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(st, S.out_done, 0));
+        if (io->out_cell_log) CK(cudaMemsetAsync(S.log.p, 0xff, (size_t)m * times * 4, st));
+        AdvectParams P = P0;
+        P.pos = (double*)S.xyz.p; P.depth = (float*)S.depth.p;
+        P.out_pos = (double*)S.out_pos.p; P.out_vel = (double*)S.out_vel.p; P.out_attr = want_attr ? (double*)S.out_attr.p : nullptr;
+        P.cell_log = io->out_cell_log ? (int*)S.log.p : nullptr;
+        P.status = io->out_status ? (int*)S.status.p : nullptr;
+        P.steps = io->out_steps ? (int*)S.steps.p : nullptr;
+        P.fcell = io->out_cell ? (int*)S.fcell.p : nullptr;
+        P.min_edge = io->out_min_edge ? (double*)S.edge.p : nullptr;
+        P.diag_edge = (cfg->count_near_edge || P.min_edge) ? 1 : 0;
+        if ((rc = run_range(ctx, cfg, path, m, io->cell0 ? (const int*)S.cell0.p : nullptr, (int*)S.cell_int.p, S.vals, S.vals2, S.keys2,
+                            S.tmp, P, nullptr, nullptr, ctx->chunk_ev[2 * k], ctx->chunk_ev[2 * k + 1])))
+            return rc;
+        CK(cudaEventRecord(S.k_done, st));
+        if (k >= 1 && (rc = copy_out(k - 1))) return rc;
+    }
+    if ((rc = copy_out(nchunks - 1))) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->pipe[0].out_done, 0));
+    if (nchunks > 1) CK(cudaStreamWaitEvent(st, ctx->pipe[1].out_done, 0));
+    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev_end, st));
+    CK(cudaStreamSynchronize(st));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->particle_steps = (int64_t)h_counters[0];
+        stats->alive_at_end = (int64_t)h_counters[1];
+        stats->near_edge_particles = (int64_t)h_counters[3];
+        float ms = 0.f;
+        for (int k = 0; k < nchunks; ++k)
+            if (cudaEventElapsedTime(&ms, ctx->chunk_ev[2 * k], ctx->chunk_ev[2 * k + 1]) == cudaSuccess) stats->kernel_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_end) == cudaSuccess) stats->total_ms = ms;
+        stats->launches = (int32_t)(ctx->launches - launches0);
+    }
+    return MOPS_OK;
+}
+
 int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back, const mops_traj_io* io, mops_traj_stats* stats,
                     bool path)
 {
@@ -461,6 +617,37 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     int attr_count = 0;
     if (path && F.n_attr_total > 1) attr_count = std::min(std::min(F.n_attr, B.n_attr), MOPS_MAX_ATTRS);
     const bool want_attr = path && attr_count > 0 && io->out_attr;
+
+    AdvectParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.rec = ctx->rec; P.c4 = ctx->c4; P.c_int2ext = ctx->c_int2ext; P.nC = ctx->nC; P.L = F.L;
+    P.sv[0] = view_of(F); P.sv[1] = view_of(B);
+    P.attr_count = attr_count;
+    P.use_euler = (cfg->method == MOPS_METHOD_EULER) ? 1 : 0;
+    P.delta_t = (cfg->direction == MOPS_DIR_FORWARD ? 1 : -1) * (int)cfg->delta_t;
+    P.times = times; P.each = each; P.record_t = (int)cfg->record_t;
+    P.record_interval = (int)(cfg->record_t / cfg->delta_t);
+    P.duration = (double)cfg->duration;
+    P.walk = (cfg->semantics == MOPS_SEM_WALK) ? 1 : 0;
+    P.counters = ctx->counters;
+
+    // HOST-mode calls, opt-in (MOPS_HOST_CHUNK=<particles>): chunked three-stream pipeline, copies overlap
+    // the kernels.  Chunks are caller-order ranges (results must land in caller order), so it only pays when
+    // the caller's seeds are already spatially coherent: with the bench's uniformly random 64 M seeds a 4 M
+    // chunk has 1.5 particles per cell instead of 24 and the kernels slow down by more than the copies cost
+    // (B200, per step: single pass 3.49 s; 16 M chunks 4.07 s; 8 M 4.81 s; 4 M 6.03 s; 2 M 7.87 s), hence off
+    // by default.
+    {
+        long long chunk = 0;
+        if (const char* e = getenv("MOPS_HOST_CHUNK")) chunk = atoll(e);
+        if (host && chunk > 0 && n > chunk && !getenv("MOPS_ZERO_COPY")) {
+            rc = trajectory_host_pipelined(ctx, cfg, path, io, stats, P, each, times, want_attr, chunk, launches0);
+            if (rc) return rc;
+            if ((rc = mark_use(ctx, front))) return rc;
+            if (path && back != front && (rc = mark_use(ctx, back))) return rc;
+            return MOPS_OK;
+        }
+    }
 
     const size_t out_bytes = (size_t)n * each * 3 * sizeof(double);
     double *d_xyz, *d_out_pos, *d_out_vel, *d_out_attr = nullptr;
@@ -518,66 +705,16 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     // (the kernel writes every output slot itself, zeros included -- see k_advect)
     if (d_log) CK(cudaMemsetAsync(d_log, 0xff, (size_t)n * times * 4, st));
 
-    // start cells in internal numbering
     if ((rc = ensure(ctx, ctx->p_cell_int, (size_t)n * 4))) return rc;
-    int* d_cell_int = (int*)ctx->p_cell_int.p;
-    CK(cudaEventRecord(ctx->ev2, st));
-    if (d_cell0_ext) {
-        k_map_ids<<<blocks_for(n, 256), 256, 0, st>>>(d_cell0_ext, d_cell_int, ctx->c_ext2int, ctx->nC, n);
-        ctx->launches++;
-    } else {
-        dispatch_locate(ctx, n, d_xyz, d_cell_int, nullptr);
-    }
-    CK(cudaEventRecord(ctx->ev3, st));
-
-    // processing order: particles sorted by (Morton-numbered) start cell
-    const int* d_order = nullptr;
-    if (cfg->sort_particles && n > 1) {
-        if ((rc = ensure(ctx, ctx->s_vals, (size_t)n * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->s_keys2, (size_t)n * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->s_vals2, (size_t)n * 4))) return rc;
-        k_iota<<<blocks_for(n, 256), 256, 0, st>>>((int*)ctx->s_vals.p, n);
-        ctx->launches++;
-        int bits = 1;
-        while ((1LL << bits) < (long long)ctx->nC + 1 && bits < 31) ++bits;
-        size_t tmp_bytes = 0;
-        // keys are cell ids in [-1, nC): bias by +1 is unnecessary because -1 (invalid) sorts last as unsigned
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned*)d_cell_int, (unsigned*)ctx->s_keys2.p,
-                                        (const int*)ctx->s_vals.p, (int*)ctx->s_vals2.p, (int)n, 0, 32, st);
-        if ((rc = ensure(ctx, ctx->s_tmp, tmp_bytes))) return rc;
-        CK(cub::DeviceRadixSort::SortPairs(ctx->s_tmp.p, tmp_bytes, (const unsigned*)d_cell_int, (unsigned*)ctx->s_keys2.p,
-                                           (const int*)ctx->s_vals.p, (int*)ctx->s_vals2.p, (int)n, 0, 32, st));
-        (void)bits;
-        d_order = (const int*)ctx->s_vals2.p;
-    }
-
     CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
-    AdvectParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.rec = ctx->rec; P.c4 = ctx->c4; P.c_int2ext = ctx->c_int2ext; P.nC = ctx->nC; P.L = F.L;
-    P.sv[0] = view_of(F); P.sv[1] = view_of(B);
-    P.attr_count = attr_count;
-    P.use_euler = (cfg->method == MOPS_METHOD_EULER) ? 1 : 0;
-    P.delta_t = (cfg->direction == MOPS_DIR_FORWARD ? 1 : -1) * (int)cfg->delta_t;
-    P.times = times; P.each = each; P.record_t = (int)cfg->record_t;
-    P.record_interval = (int)(cfg->record_t / cfg->delta_t);
-    P.duration = (double)cfg->duration;
-    P.n = n; P.order = d_order;
-    P.pos = d_xyz; P.depth = d_depth; P.cell0 = d_cell_int;
+    P.pos = d_xyz; P.depth = d_depth;
     P.out_pos = d_out_pos; P.out_vel = d_out_vel; P.out_attr = d_out_attr;
     P.cell_log = d_log; P.status = d_status; P.steps = d_steps; P.fcell = d_fcell;
     P.min_edge = d_edge;
     P.diag_edge = (cfg->count_near_edge || d_edge) ? 1 : 0;
-    P.walk = (cfg->semantics == MOPS_SEM_WALK) ? 1 : 0;
-    P.counters = ctx->counters;
-
-    CK(cudaEventRecord(ctx->ev1, st));
-    switch (ctx->M) {
-    case 6: launch_advect<6>(ctx, P, path); break;
-    case 8: launch_advect<8>(ctx, P, path); break;
-    default: launch_advect<20>(ctx, P, path); break;
-    }
-    CK(cudaGetLastError());
+    if ((rc = run_range(ctx, cfg, path, n, d_cell0_ext, (int*)ctx->p_cell_int.p, ctx->s_vals, ctx->s_vals2, ctx->s_keys2, ctx->s_tmp, P,
+                        ctx->ev2, ctx->ev3, ctx->ev1, nullptr)))
+        return rc;
     CK(cudaEventRecord(ctx->ev_kend, st));
     if ((rc = mark_use(ctx, front))) return rc;
     if (path && back != front && (rc = mark_use(ctx, back))) return rc;
@@ -737,6 +874,12 @@ int mops_create(mops_ctx** out, int device_ordinal)
               cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess;
     ctx->stream = ctx->own_stream;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i)
+        ok = cudaEventCreateWithFlags(&ctx->pipe[i].in_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->pipe[i].k_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->pipe[i].out_done, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->marks[i]) == cudaSuccess;
     for (int i = 0; ok && i < MOPS_MAX_SNAPSHOT_SLOTS; ++i) {
         ok = cudaEventCreate(&ctx->snap[i].ready) == cudaSuccess && cudaEventCreate(&ctx->snap[i].last_use) == cudaSuccess;
@@ -765,6 +908,17 @@ void mops_destroy(mops_ctx* ctx)
                    &ctx->p_out_attr, &ctx->p_log, &ctx->p_status, &ctx->p_steps, &ctx->p_fcell, &ctx->p_edge, &ctx->s_keys, &ctx->s_vals,
                    &ctx->s_keys2, &ctx->s_vals2, &ctx->s_tmp, &ctx->r_img0, &ctx->r_img1, &ctx->r_cells};
     for (Buf* b : bufs) cudaFree(b->p);
+    for (auto& ps : ctx->pipe) {
+        Buf* pb[] = {&ps.xyz, &ps.depth, &ps.cell0, &ps.cell_int, &ps.vals, &ps.vals2, &ps.keys2, &ps.tmp, &ps.out_pos, &ps.out_vel,
+                     &ps.out_attr, &ps.log, &ps.status, &ps.steps, &ps.fcell, &ps.edge};
+        for (Buf* b : pb) cudaFree(b->p);
+        if (ps.in_done) cudaEventDestroy(ps.in_done);
+        if (ps.k_done) cudaEventDestroy(ps.k_done);
+        if (ps.out_done) cudaEventDestroy(ps.out_done);
+    }
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     cudaFree(ctx->counters);
     cudaFree(ctx->d_nonmono);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);

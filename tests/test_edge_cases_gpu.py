@@ -117,3 +117,33 @@ def test_attribute_gating(ctx):
     assert np.array_equal(g["raw_pos"], w["raw_pos"])
     img = e.remap(2, 32, 16, depth=250.0)
     assert img["img1"] is None and P.remap(m, P.prepare(m, a), 32, 16, depth=250.0)["img1"] is None
+
+
+@pytest.mark.parametrize("chunk", [257, 1000, 4999])
+def test_host_pipeline_chunks_match_single_pass(ctx, chunk, monkeypatch):
+    """HOST-mode calls above MOPS_HOST_CHUNK particles run as a three-stream chunk pipeline; every output
+    (records, attributes, cell log, status, steps, final cell, edge distance, end points, counters) must be
+    bit-identical to the single-pass call, for ragged last chunks, given and device-located start cells."""
+    e, P, m, p0, p1, capi = ctx
+    seeds = cases.seeds_random(5000, seed=21)
+    seeds[17] = np.nan
+    depths = np.linspace(5.0, 900.0, 5000).astype(np.float32)
+    cells = P.locate(m, seeds)
+    cells[40::97] = -1
+    for cell0 in (cells, None):
+        monkeypatch.delenv("MOPS_HOST_CHUNK", raising=False)
+        a = e.pathline(0, 1, seeds, 300, 21600, 3600, depths=depths, cell0=cell0, log_cells=True, near_edge=True)
+        monkeypatch.setenv("MOPS_HOST_CHUNK", str(chunk))
+        b = e.pathline(0, 1, seeds, 300, 21600, 3600, depths=depths, cell0=cell0, log_cells=True, near_edge=True)
+        for k in ("raw_pos", "raw_vel", "raw_attr", "pos", "depth", "cell_log", "status", "steps_alive", "final_cell", "min_edge"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        for f in ("particle_steps", "alive_at_end", "near_edge_particles"):
+            assert int(getattr(a["stats"], f)) == int(getattr(b["stats"], f)), f
+        assert b["stats"].launches > a["stats"].launches and b["stats"].kernel_ms > 0
+    monkeypatch.setenv("MOPS_HOST_CHUNK", str(chunk))
+    s1 = e.streamline(0, seeds, 300, 21600, 1800, depth=300.0)
+    monkeypatch.delenv("MOPS_HOST_CHUNK")
+    s0 = e.streamline(0, seeds, 300, 21600, 1800, depth=300.0)
+    assert np.array_equal(s0["raw_pos"], s1["raw_pos"], equal_nan=True) and np.array_equal(s0["raw_vel"], s1["raw_vel"], equal_nan=True)
+    want = P.streamline(m, p0, seeds, P.locate(m, seeds), 300, 21600, 1800, depth=300.0)
+    assert np.array_equal(s1["raw_pos"], want["raw_pos"], equal_nan=True)
