@@ -84,6 +84,10 @@ struct mops_ctx {
     } pipe[2];
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> chunk_ev; // (kernel start, kernel end) pairs, grown on demand
+    // kd-tree over the cell centres, only for meshes with removed cells (see kd_nearest)
+    double4* kd_pts = nullptr;
+    unsigned char* kd_dim = nullptr;
+    int kd_n = 0;
 };
 
 namespace {
@@ -231,6 +235,8 @@ void free_mesh(mops_ctx* c)
     }
     cudaFree(c->rec); cudaFree(c->c4); cudaFree(c->trig); cudaFree(c->vert); cudaFree(c->vcell_ext);
     cudaFree(c->c_int2ext); cudaFree(c->c_ext2int); cudaFree(c->v_int2ext); cudaFree(c->v_ext2int);
+    cudaFree(c->kd_pts); cudaFree(c->kd_dim);
+    c->kd_pts = nullptr; c->kd_dim = nullptr; c->kd_n = 0;
     c->cube = nullptr; c->rec = nullptr; c->c4 = nullptr; c->trig = nullptr; c->vert = nullptr; c->vcell_ext = nullptr;
     c->c_int2ext = c->c_ext2int = c->v_int2ext = c->v_ext2int = nullptr;
     c->has_mesh = false;
@@ -368,11 +374,19 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
     return MOPS_OK;
 }
 
+inline KdView kd_view(const mops_ctx* ctx)
+{
+    KdView v;
+    v.pts = ctx->kd_pts; v.dim = ctx->kd_dim; v.n = ctx->kd_n;
+    return v;
+}
+
 template <int M>
 void launch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cell_int, int* d_cell_ext)
 {
     k_locate<M><<<blocks_for(n * 8, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const CellRec<M>*>(ctx->rec), ctx->c4, ctx->cube,
-                                                                 ctx->F, ctx->nC, n, d_xyz, d_cell_int, d_cell_ext, ctx->c_int2ext);
+                                                                 ctx->F, ctx->nC, kd_view(ctx), n, d_xyz, d_cell_int, d_cell_ext,
+                                                                 ctx->c_int2ext);
     ctx->launches++;
 }
 
@@ -800,6 +814,7 @@ int view_impl(mops_ctx* ctx, const mops_view_cfg* cfg, int slot, double* img, in
     ViewParams P;
     std::memset(&P, 0, sizeof(P));
     P.rec = ctx->rec; P.c4 = ctx->c4; P.cube = ctx->cube; P.c_int2ext = ctx->c_int2ext; P.F = ctx->F; P.nC = ctx->nC; P.L = S.L;
+    P.kd = kd_view(ctx);
     P.s = view_of(S);
     P.width = cfg->width; P.height = cfg->height;
     P.minLat = cfg->lat_min; P.maxLat = cfg->lat_max; P.minLon = cfg->lon_min; P.maxLon = cfg->lon_max;
@@ -980,6 +995,50 @@ int mops_elapsed_ms(mops_ctx* ctx, int32_t idx_from, int32_t idx_to, double* ms_
     return MOPS_OK;
 }
 
+// median-split kd-tree over the cell centres (internal numbering) in the implicit layout kd_nearest walks
+static void build_kd(const std::vector<double4>& c4, std::vector<double4>& pts, std::vector<unsigned char>& dims)
+{
+    const int n = (int)c4.size();
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    dims.assign(n, 0);
+    std::vector<std::pair<int, int>> todo;
+    todo.emplace_back(0, n);
+    while (!todo.empty()) {
+        const int lo = todo.back().first, hi = todo.back().second;
+        todo.pop_back();
+        if (hi - lo <= 0) continue;
+        const int mid = (lo + hi) >> 1;
+        if (hi - lo > 1) {
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            for (int i = lo; i < hi; ++i) {
+                const double4& p = c4[idx[i]];
+                const double v[3] = {p.x, p.y, p.z};
+                for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], v[a]); mx[a] = std::max(mx[a], v[a]); }
+            }
+            int ax = 0;
+            if (mx[1] - mn[1] > mx[ax] - mn[ax]) ax = 1;
+            if (mx[2] - mn[2] > mx[ax] - mn[ax]) ax = 2;
+            std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
+                const double va = ax == 0 ? c4[a].x : ax == 1 ? c4[a].y : c4[a].z;
+                const double vb = ax == 0 ? c4[b].x : ax == 1 ? c4[b].y : c4[b].z;
+                return va < vb;
+            });
+            dims[mid] = (unsigned char)ax;
+            todo.emplace_back(lo, mid);
+            todo.emplace_back(mid + 1, hi);
+        }
+    }
+    pts.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const double4& p = c4[idx[i]];
+        long long id = idx[i];
+        double w;
+        std::memcpy(&w, &id, 8);
+        pts[i] = make_double4(p.x, p.y, p.z, w);
+    }
+}
+
 int mops_set_mesh(mops_ctx* ctx, int32_t n_cells, int32_t n_vertices, int32_t max_edges, const double* cell_xyz,
                   const double* vertex_xyz, const int32_t* vertices_on_cell, const int32_t* cells_on_cell,
                   const int32_t* cells_on_vertex, const int32_t* n_edges_on_cell)
@@ -1027,6 +1086,26 @@ int mops_set_mesh(mops_ctx* ctx, int32_t n_cells, int32_t n_vertices, int32_t ma
     for (size_t i = 0; i < nC; ++i) {
         const size_t e = (size_t)c_int2ext[i];
         h_c4[i] = make_double4(cell_xyz[3 * e], cell_xyz[3 * e + 1], cell_xyz[3 * e + 2], 0.0);
+    }
+    // culled mesh (a neighbour of some cell was removed)?  Then the greedy walk is not exact on its own.
+    bool culled = false;
+    for (size_t c = 0; c < nC && !culled; ++c) {
+        const int nv = std::min((int)n_edges_on_cell[c], (int)max_edges);
+        for (int k = 0; k < nv; ++k) {
+            const long long e = (long long)cells_on_cell[c * (size_t)max_edges + k] - 1;
+            if (e < 0 || e >= (long long)n_cells) { culled = true; break; }
+        }
+    }
+    if (culled) {
+        std::vector<double4> kd_pts;
+        std::vector<unsigned char> kd_dim;
+        build_kd(h_c4, kd_pts, kd_dim);
+        CK(cudaMalloc(&ctx->kd_pts, nC * sizeof(double4)));
+        CK(cudaMalloc(&ctx->kd_dim, nC));
+        CK(cudaMemcpy(ctx->kd_pts, kd_pts.data(), nC * sizeof(double4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->kd_dim, kd_dim.data(), nC, cudaMemcpyHostToDevice));
+        ctx->kd_n = n_cells;
+        ctx->mesh_bytes += nC * (sizeof(double4) + 1);
     }
     std::vector<VertRec> h_vert(nV);
     std::vector<int> h_vcell(nV * 3);
@@ -1226,6 +1305,7 @@ int mops_remap_fixed_depth(mops_ctx* ctx, const mops_remap_cfg* cfg, int32_t slo
     RemapParams P;
     std::memset(&P, 0, sizeof(P));
     P.rec = ctx->rec; P.c4 = ctx->c4; P.cube = ctx->cube; P.c_int2ext = ctx->c_int2ext; P.F = ctx->F; P.nC = ctx->nC; P.L = S.L;
+    P.kd = kd_view(ctx);
     P.s = view_of(S);
     P.attr_count = S.n_attr; P.attr_image = attr_image ? 1 : 0;
     P.width = cfg->width; P.height = cfg->height;

@@ -582,6 +582,45 @@ __device__ __forceinline__ int walk_nearest(const CellRec<M>* __restrict__ rec, 
     return cur;
 }
 
+// ---- exact 1-NN over the cell centres for meshes with removed (land) cells ----------------------
+// On a culled mesh the greedy cellsOnCell walk can stop at a local minimum behind a coast, and a query on
+// land has no containing cell at all.  A host-built kd-tree (median splits, implicit layout: the node of
+// range [lo,hi) is element (lo+hi)/2, children [lo,mid) and (mid,hi)) gives the same answer as the
+// reference's nanoflann search (src/Core/MPASOGrid.cpp:287-313) for those queries.
+struct KdView {
+    const double4* pts;       // tree order; .w carries the (internal) cell id bits
+    const unsigned char* dim; // split axis of each node
+    int n;                    // 0: closed mesh, the walk alone is exact
+};
+
+__device__ __noinline__ int kd_nearest(const KdView kd, double qx, double qy, double qz, int best, double dbest)
+{
+    int s_lo[40], s_hi[40];
+    double s_b[40];
+    int sp = 0;
+    s_lo[0] = 0; s_hi[0] = kd.n; s_b[0] = 0.0; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int lo = s_lo[sp], hi = s_hi[sp];
+        if (!(s_b[sp] < dbest)) continue; // nothing beyond that plane can be strictly closer
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double4 p = kd.pts[mid];
+            const double d = dist2(qx, qy, qz, p.x, p.y, p.z);
+            const int id = (int)__double_as_longlong(p.w);
+            if (d < dbest || (d == dbest && id < best)) { dbest = d; best = id; }
+            const int ax = kd.dim[mid];
+            const double diff = (ax == 0) ? qx - p.x : (ax == 1) ? qy - p.y : qz - p.z;
+            int flo, fhi;
+            if (diff < 0.0) { flo = mid + 1; fhi = hi; hi = mid; }
+            else            { flo = lo; fhi = mid; lo = mid + 1; }
+            const double b = diff * diff;
+            if (flo < fhi && b < dbest && sp < 40) { s_lo[sp] = flo; s_hi[sp] = fhi; s_b[sp] = b; ++sp; }
+        }
+    }
+    return best;
+}
+
 // direction -> cube-map bucket (start guess of the walk; float precision is enough)
 __device__ __forceinline__ int cube_bucket(double x, double y, double z, int F)
 {
@@ -608,6 +647,21 @@ __device__ __forceinline__ void cube_center(int face, int i, int j, int F, doubl
     if (face < 2)      { x = s; y = u; z = v; }
     else if (face < 4) { x = u; y = s; z = v; }
     else               { x = u; y = v; z = s; }
+}
+
+// point location as the reference defines it (nearest cell centre): cube-map start + greedy walk; on a
+// culled mesh the answer is accepted only when the point lies inside that cell's polygon, otherwise the
+// kd-tree decides.
+template <int M>
+__device__ __forceinline__ int locate_cell(const CellRec<M>* __restrict__ rec, const double4* __restrict__ c4, const int* __restrict__ cube,
+                                           int F, const KdView kd, double qx, double qy, double qz)
+{
+    int c = walk_nearest<M>(rec, c4, cube[cube_bucket(qx, qy, qz, F)], qx, qy, qz);
+    if (kd.n > 0 && !in_mesh<M>(rec + c, rec[c].nv, qx, qy, qz)) {
+        const double4 cc = c4[c];
+        c = kd_nearest(kd, qx, qy, qz, c, dist2(qx, qy, qz, cc.x, cc.y, cc.z));
+    }
+    return c;
 }
 
 } // namespace mops

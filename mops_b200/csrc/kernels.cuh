@@ -111,7 +111,7 @@ __global__ void k_cube_level(const CellRec<M>* __restrict__ rec, const double4* 
 // =========================================================================================
 template <int M>
 __global__ void __launch_bounds__(256) k_locate(const CellRec<M>* __restrict__ rec, const double4* __restrict__ c4,
-                                                const int* __restrict__ cube, int F, int nC,
+                                                const int* __restrict__ cube, int F, int nC, const KdView kd,
                                                 long long n, const double* __restrict__ xyz,
                                                 int* __restrict__ cell_int, int* __restrict__ cell_ext,
                                                 const int* __restrict__ c_int2ext)
@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(256) k_locate(const CellRec<M>* __restrict__ r
             dcur = dbest;
         }
         result = cur;
+        // culled mesh: accept only a cell that contains the query, else exact kd search (lane 0 decides)
+        if (kd.n > 0 && sub == 0 && !in_mesh<M>(rec + cur, rec[cur].nv, qx, qy, qz)) result = kd_nearest(kd, qx, qy, qz, cur, dcur);
     }
     if (sub == 0) {
         if (cell_int) cell_int[gid] = result;
@@ -556,6 +558,7 @@ struct RemapParams {
     const void* rec;
     const double4* c4;
     const int* cube;
+    KdView kd;
     const int* c_int2ext;
     int F, nC, L;
     SnapView s;
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(128) k_remap(const RemapParams P)
     const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
     const double nanv = nan("");
     int cell = -1;
-    if (finite3(pos.x, pos.y, pos.z)) cell = walk_nearest<M>(recs, P.c4, P.cube[cube_bucket(pos.x, pos.y, pos.z, P.F)], pos.x, pos.y, pos.z);
+    if (finite3(pos.x, pos.y, pos.z)) cell = locate_cell<M>(recs, P.c4, P.cube, P.F, P.kd, pos.x, pos.y, pos.z);
     if (P.pixel_cell) P.pixel_cell[gid] = cell >= 0 ? P.c_int2ext[cell] : -1;
 
     bool ok = (cell >= 0 && cell < P.nC);
@@ -707,6 +710,7 @@ struct ViewParams {
     const void* rec;
     const double4* c4;
     const int* cube;
+    KdView kd;
     const int* c_int2ext;
     int F, nC, L;
     SnapView s;
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(128) k_view(const ViewParams P)
 
     const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
     int cell = -1;
-    if (finite3(pos.x, pos.y, pos.z)) cell = walk_nearest<M>(recs, P.c4, P.cube[cube_bucket(pos.x, pos.y, pos.z, P.F)], pos.x, pos.y, pos.z);
+    if (finite3(pos.x, pos.y, pos.z)) cell = locate_cell<M>(recs, P.c4, P.cube, P.F, P.kd, pos.x, pos.y, pos.z);
     if (P.pixel_cell) P.pixel_cell[gid] = cell >= 0 ? P.c_int2ext[cell] : -1;
 
     bool ok = (cell >= 0 && cell < P.nC);

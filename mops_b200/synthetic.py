@@ -423,3 +423,43 @@ def random_sphere_points(n: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     p = rng.normal(size=(n, 3))
     return p / np.linalg.norm(p, axis=1, keepdims=True)
+
+
+def carve_land(mesh: Mesh, keep: np.ndarray) -> Mesh:
+    """Ocean-only sub-mesh the way MPAS's cell culler leaves it: cells with keep == False are removed, the
+    vertices of the kept cells stay (coast vertices included), ids are renumbered densely, and every
+    reference to a removed cell becomes 0 in cellsOnCell / cellsOnVertex (the boundary markers the reference
+    tests in MPASOSolutionTBB.cpp:33-40 and skips in MPASOVisualizerKernels.cpp:908-911)."""
+    keep = np.asarray(keep, dtype=bool)
+    assert keep.shape == (mesh.n_cells,) and keep.any()
+    new_cell = np.zeros(mesh.n_cells + 1, dtype=np.int64)        # 1-based old -> 1-based new, 0 = none
+    new_cell[1:][keep] = np.arange(1, keep.sum() + 1)
+    voc = mesh.vertices_on_cell[keep]
+    used = np.zeros(mesh.n_vertices + 1, dtype=bool)
+    used[voc.ravel()] = True
+    used[0] = False
+    new_vert = np.zeros(mesh.n_vertices + 1, dtype=np.int64)
+    new_vert[used] = np.arange(1, used.sum() + 1)
+    return Mesh(n_cells=int(keep.sum()), n_vertices=int(used.sum()), max_edges=mesh.max_edges,
+                cell_xyz=np.ascontiguousarray(mesh.cell_xyz[keep]),
+                vertex_xyz=np.ascontiguousarray(mesh.vertex_xyz[used[1:]]),
+                vertices_on_cell=new_vert[voc].astype(np.int32),
+                cells_on_cell=new_cell[mesh.cells_on_cell[keep]].astype(np.int32),
+                cells_on_vertex=new_cell[mesh.cells_on_vertex[used[1:]]].astype(np.int32),
+                n_edges_on_cell=mesh.n_edges_on_cell[keep].copy(), level=mesh.level)
+
+
+def continents_mask(mesh: Mesh, seed: int = 3, n_blobs: int = 7, frac: float = 0.3) -> np.ndarray:
+    """keep-mask with irregular 'continents': union of spherical caps and a meridional wall with a gap (so
+    the ocean is non-convex and has narrow straits); about `frac` of the cells are land."""
+    rng = np.random.default_rng(seed)
+    u = mesh.cell_xyz / np.linalg.norm(mesh.cell_xyz, axis=1, keepdims=True)
+    land = np.zeros(mesh.n_cells, dtype=bool)
+    centres = rng.normal(size=(n_blobs, 3))
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    radii = rng.uniform(0.15, 0.45, n_blobs) * np.sqrt(frac / 0.3)
+    for c, r in zip(centres, radii):
+        land |= np.arccos(np.clip(u @ c, -1, 1)) < r
+    lat = np.arcsin(u[:, 2]); lon = np.arctan2(u[:, 1], u[:, 0])
+    land |= (np.abs(lon - 0.5) < 0.06) & (np.abs(lat) < 1.0) & (np.abs(lat - 0.2) > 0.05)   # wall with a strait
+    return ~land

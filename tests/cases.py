@@ -61,3 +61,17 @@ def voronoi_snapshots(kind: str, n_levels: int):
     m = voronoi_mesh(kind)
     return (S.solid_body_snapshot(m, n_levels, 2.0, tilt=0.3, shear=0.4, bumpy=0.3, w_amp=2e-3, with_attrs=True),
             S.solid_body_snapshot(m, n_levels, 3.0, tilt=0.35, shear=0.2, bumpy=0.25, w_amp=-1e-3, with_attrs=True))
+
+
+@functools.lru_cache(maxsize=None)
+def ocean_mesh(level: int = 4):
+    """culled (ocean-only) mesh: continents, a meridional wall with a strait; cellsOnCell / cellsOnVertex hold
+    0 where the neighbour was removed"""
+    return S.carve_land(mesh(level), S.continents_mask(mesh(level)))
+
+
+@functools.lru_cache(maxsize=None)
+def ocean_snapshots(level: int, n_levels: int):
+    m = ocean_mesh(level)
+    return (S.solid_body_snapshot(m, n_levels, 2.0, tilt=0.3, shear=0.4, bumpy=0.3, w_amp=2e-3, with_attrs=True),
+            S.solid_body_snapshot(m, n_levels, 3.0, tilt=0.35, shear=0.2, bumpy=0.25, w_amp=-1e-3, with_attrs=True))

@@ -139,3 +139,42 @@ def test_general_voronoi_meshes(kind):
         assert _same(ri["img0"], bi["img0"]) and _same(ri["img1"], bi["img1"])
     finally:
         o.close()
+
+
+def test_ocean_mesh_with_land_boundaries():
+    """culled mesh (0 entries in cellsOnCell / cellsOnVertex): boundary vertices in the preprocessing, seeds
+    on land (nearest ocean cell, then IsInMesh fails), trajectories running into the coast, land pixels"""
+    m = cases.ocean_mesh(4)
+    s0, s1 = cases.ocean_snapshots(4, 9)
+    assert (m.cells_on_vertex == 0).sum() > 100
+    o = R.RefOracle(m, [s0, s1])
+    try:
+        p0, p1 = P.prepare(m, s0), P.prepare(m, s1)
+        for sid, p in ((0, p0), (1, p1)):
+            r = o.prepared(sid)
+            assert _same(p.ztop_v, r["ztop_vertex"]) and _same(p.vel_v, r["vel_vertex"]) and _same(p.w_v, r["vertvel_vertex"])
+            for name in s0.attrs:
+                assert _same(p.attrs_v[name], o.prepared_attr(sid, name))
+        seeds = cases.seeds_random(3000, seed=12)
+        cells = o.locate(seeds)
+        assert _same(P.locate(m, seeds), cells)
+        rr = o.streamline(seeds, 600, 86400 * 2, 3600, depth=300.0, method="rk4")
+        b = P.streamline(m, p0, seeds, cells, 600, 86400 * 2, 3600, depth=300.0, method="rk4")
+        f = P.finalize_lines(seeds, b["raw_pos"], b["raw_vel"])
+        assert _same(rr["points"], f["points"]) and _same(rr["velocity"], f["velocity"])
+        st = b["status"]
+        assert (st == 0).sum() > 500 and (st != 0).sum() > 500      # survivors and coast / land casualties
+        o.activate(0, 1)
+        rr = o.pathline(seeds, 600, 86400, 3600, depth=300.0, method="rk4")
+        b = P.pathline(m, p0, p1, seeds, cells, 600, 86400, 3600, depth=300.0, method="rk4")
+        f = P.finalize_lines(seeds, b["raw_pos"], b["raw_vel"], pathline_mode=True)
+        assert _same(rr["points"], f["points"]) and _same(rr["velocity"], f["velocity"])
+        o.activate(0, None)
+        ri, bi = o.remap(90, 45, depth=300.0), P.remap(m, p0, 90, 45, depth=300.0)
+        assert _same(ri["img0"], bi["img0"]) and _same(ri["img1"], bi["img1"])
+        nan_frac = np.isnan(bi["img0"][..., 0]).mean()
+        assert 0.1 < nan_frac < 0.6
+        pos = P.pixel_positions(90, 45)
+        assert _same(o.locate(pos.reshape(-1, 3)).reshape(45, 90), bi["pixel_cell"])
+    finally:
+        o.close()

@@ -371,3 +371,54 @@ def test_general_voronoi_meshes_wide_records(eng, P, kind, width):
     wl = P.regrid_fixed_latitude(m, p0, 60, 20, 10.0, 500.0, 4000.0)
     gl = eng.regrid_fixed_latitude(0, 60, 20, 10.0, 500.0, 4000.0)
     assert np.allclose(gl["img"], wl["img"], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("level", [4, 6])
+def test_culled_ocean_mesh_with_land(eng, P, level):
+    """mesh with removed (land) cells: the greedy walk alone is not exact there, the kd-tree fallback must give
+    the reference's nearest-centre answer for seeds on land, behind peninsulas and in straits; boundary
+    vertices in the preprocessing; trajectories running into the coast; land pixels in every view"""
+    m = cases.ocean_mesh(level)
+    s0, s1 = cases.ocean_snapshots(level, 9)
+    eng.set_mesh(m)
+    eng.set_snapshot(0, s0)
+    eng.set_snapshot(1, s1)
+    p0, p1 = P.prepare(m, s0), P.prepare(m, s1)
+    got = eng.get_prepared(0, attrs=2)
+    assert np.array_equal(got["ztop_vertex"], p0.ztop_v) and np.array_equal(got["vel_vertex"], p0.vel_v)
+    names = sorted(s0.attrs)
+    assert np.array_equal(got["attr0"], p0.attrs_v[names[0]]) and np.array_equal(got["attr1"], p0.attrs_v[names[1]])
+    seeds = cases.seeds_random(20000 if level == 6 else 4000, seed=12)
+    cells = P.locate(m, seeds)
+    gc = eng.locate(seeds)
+    assert np.array_equal(gc, cells), f"{(gc != cells).sum()} of {len(cells)} differ"
+    import torch
+    dc = eng.locate(torch.from_numpy(seeds).cuda())   # device buffers: asynchronous on the engine's stream
+    eng.synchronize()
+    assert np.array_equal(dc.cpu().numpy(), cells)
+    n = 4000
+    want = P.streamline(m, p0, seeds[:n], cells[:n], 600, 2 * 86400, 3600, depth=300.0)
+    g = eng.streamline(0, seeds[:n], 600, 2 * 86400, 3600, depth=300.0, log_cells=True)   # device-located start cells
+    assert np.array_equal(g["cell_log"], want["cell_log"]) and np.array_equal(g["status"], want["status"])
+    assert np.array_equal(g["raw_pos"], want["raw_pos"]) and np.array_equal(g["raw_vel"], want["raw_vel"])
+    assert (want["status"] == 0).sum() > 50 and (want["status"] != 0).sum() > 500
+    want = P.pathline(m, p0, p1, seeds[:n], cells[:n], 600, 86400, 3600, depth=300.0)
+    g = eng.pathline(0, 1, seeds[:n], 600, 86400, 3600, depth=300.0, cell0=cells[:n], log_cells=True)
+    assert np.array_equal(g["cell_log"], want["cell_log"]) and np.array_equal(g["raw_pos"], want["raw_pos"])
+    assert np.array_equal(g["raw_attr"], want["raw_attr"])
+    wi = P.remap(m, p0, 180, 90, depth=300.0)
+    gi = eng.remap(0, 180, 90, depth=300.0)
+    assert np.array_equal(gi["pixel_cell"], wi["pixel_cell"])
+    # images go through sin/cos of the pixel's lat/lon (ENU conversion): same NaN mask, values to 1e-9 relative
+    assert np.array_equal(np.isnan(gi["img0"]), np.isnan(wi["img0"])) and np.array_equal(np.isnan(gi["img1"]), np.isnan(wi["img1"]))
+    assert np.allclose(gi["img0"], wi["img0"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.allclose(gi["img1"], wi["img1"], rtol=1e-9, atol=1e-9, equal_nan=True)
+    assert 0.1 < np.isnan(wi["img0"][..., 0]).mean() < 0.6
+    wl = P.remap_fixed_layer(m, p0, 120, 60, 2)
+    gl = eng.remap_fixed_layer(0, 120, 60, 2)
+    assert np.array_equal(gl["pixel_cell"], wl["pixel_cell"]) and np.array_equal(np.isnan(gl["img"]), np.isnan(wl["img"]))
+    assert np.allclose(gl["img"], wl["img"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    wl = P.regrid_fixed_latitude(m, p0, 90, 20, 10.0, 500.0, 4000.0)
+    gl = eng.regrid_fixed_latitude(0, 90, 20, 10.0, 500.0, 4000.0)
+    assert np.array_equal(np.isnan(gl["img"]), np.isnan(wl["img"]))
+    assert np.allclose(gl["img"], wl["img"], rtol=1e-9, atol=1e-12, equal_nan=True)
