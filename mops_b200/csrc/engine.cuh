@@ -105,7 +105,7 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
     for (int k = 0; k < M; ++k) {
         ax[k] = rec->vx[k]; ay[k] = rec->vy[k]; az[k] = rec->vz[k];
     }
-    double ar[M]; // ar[k] = area(v_k, v_(k+1)%nv, p)
+    double ar[M]; // ar[k] = area(v_k, v_(k+1)%nv, p); the M roots are independent -> one group
 #pragma unroll
     for (int k = 0; k < M; ++k) {
         if (k < nv) {
@@ -113,26 +113,35 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
             const double bx = wrap ? ax[0] : ax[(k + 1) % M];
             const double by = wrap ? ay[0] : ay[(k + 1) % M];
             const double bz = wrap ? az[0] : az[(k + 1) % M];
-            ar[k] = tri_area(ax[k], ay[k], az[k], bx, by, bz, px, py, pz);
+            ar[k] = tri_cross2(ax[k], ay[k], az[k], bx, by, bz, px, py, pz);
         } else {
-            ar[k] = 0.0;
+            ar[k] = 1.0;
         }
     }
+    sqrt_group<M>(ar);
+#pragma unroll
+    for (int k = 0; k < M; ++k) ar[k] = (k < nv) ? ar[k] * 0.5 : 0.0; // '/ 2.0' of triangle_area (exact either way)
     double prev = ar[0]; // A_i of i = 0 is area(v_(nv-1), v_0, p) = ar[nv-1]
 #pragma unroll
     for (int k = 1; k < M; ++k)
         if (k == nv - 1) prev = ar[k];
-    double sum = 0.0;
+    double den[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         if (i < nv) {
-            w[i] = rec->B[i] / (prev * ar[i]);
-            sum += w[i];
+            w[i] = rec->B[i];
+            den[i] = prev * ar[i];
             prev = ar[i];
         } else {
             w[i] = 0.0;
+            den[i] = 1.0;
         }
     }
+    div_group<M>(w, den); // w_i = B_i / (A_i * A_(i+1)), independent quotients
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+        if (i < nv) sum += w[i];
     const double recp = 1.0 / sum;
 #pragma unroll
     for (int i = 0; i < M; ++i)

@@ -397,22 +397,29 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     const int nv = r->nv;
                     double min_len = 1.7976931348623157e308;
                     int best = cell;
+                    double len[M + 1]; // the candidates' distances: independent roots, one group
+                    int cand[M + 1];
 #pragma unroll
                     for (int k = 0; k < M; ++k) {
-                        if (k < nv) {
-                            const int cid = r->nbr[k];
-                            if (cid >= 0) {
-                                const double4 cc = P.c4[cid];
-                                const double len = len3(cc.x - pos.x, cc.y - pos.y, cc.z - pos.z);
-                                if (len < min_len) { min_len = len; best = cid; }
-                            }
+                        cand[k] = (k < nv) ? r->nbr[k] : -1;
+                        if (cand[k] >= 0) {
+                            const double4 cc = P.c4[cand[k]];
+                            const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
+                            len[k] = dx * dx + dy * dy + dz * dz;
+                        } else {
+                            len[k] = 1.0;
                         }
                     }
                     {
                         const double4 cc = P.c4[cell];
-                        const double len = len3(cc.x - pos.x, cc.y - pos.y, cc.z - pos.z);
-                        if (len < min_len) { min_len = len; best = cell; }
+                        const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
+                        len[M] = dx * dx + dy * dy + dz * dz;
+                        cand[M] = cell;
                     }
+                    sqrt_group<M + 1>(len);
+#pragma unroll
+                    for (int k = 0; k <= M; ++k)
+                        if (cand[k] >= 0 && len[k] < min_len) { min_len = len[k]; best = cand[k]; }
                     if (best != cell) { cell = best; }
                     // walk mode: not limited to one ring (identical whenever the step is shorter than a cell)
                     if (EXTRA && P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
@@ -477,13 +484,32 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                 if (P.use_euler) {
                     new_pos = rotate_euler(pos, hvel, P.delta_t, r); // VK:968-972
                 } else {
-                    hvel.x = hvel.x / 6.0; hvel.y = hvel.y / 6.0; hvel.z = hvel.z / 6.0;
-                    vvel = vvel / 6.0;
-                    at0 = at0 / 6.0; at1 = at1 / 6.0;
+                    { // (s1 + 2 s2 + 2 s3 + s4) / 6.0: six quotients by one constant
+                        const double a6[6] = {hvel.x, hvel.y, hvel.z, vvel, at0, at1};
+                        double q6[6];
+                        bool ok6 = true;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            q6[i] = div_by6(a6[i]);
+                            ok6 = ok6 && dv_num_ok(a6[i]) && dv_quo_ok(q6[i], a6[i]);
+                        }
+                        if (!ok6) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) q6[i] = slow_div(a6[i], 6.0);
+                        }
+                        hvel.x = q6[0]; hvel.y = q6[1]; hvel.z = q6[2];
+                        vvel = q6[3];
+                        at0 = q6[4]; at1 = q6[5];
+                    }
                     const double tx = pos.x + hvel.x * dt, ty = pos.y + hvel.y * dt, tz = pos.z + hvel.z * dt; // VK:962-964
                     const double tl = len3(tx, ty, tz);
-                    if (tl > 1e-12) new_pos = mk3((tx / tl) * r, (ty / tl) * r, (tz / tl) * r);
-                    else new_pos = pos;
+                    if (tl > 1e-12) {
+                        double ux, uy, uz;
+                        div3(tx, ty, tz, tl, ux, uy, uz);
+                        new_pos = mk3(ux * r, uy * r, uz * r);
+                    } else {
+                        new_pos = pos;
+                    }
                 }
 
                 if (first_vel) { // VK:988-991 / VK:1449-1456
@@ -500,7 +526,11 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                 const double r_new = (1.0 < r_sum) ? r_sum : 1.0;
                 depth_f = (float)new_depth;
                 const double nlen = len3(new_pos);
-                if (nlen > 1e-12) new_pos = mk3((new_pos.x / nlen) * r_new, (new_pos.y / nlen) * r_new, (new_pos.z / nlen) * r_new);
+                if (nlen > 1e-12) {
+                    double ux, uy, uz;
+                    div3(new_pos.x, new_pos.y, new_pos.z, nlen, ux, uy, uz);
+                    new_pos = mk3(ux * r_new, uy * r_new, uz * r_new);
+                }
                 pos = new_pos;
 
                 bool rec_now;
