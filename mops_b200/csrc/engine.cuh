@@ -79,9 +79,12 @@ __device__ __noinline__ double min_edge_angle(const CellRec<M>* __restrict__ rec
 }
 
 // TBBKernel::IsInMesh on the precomputed edge normals (TK:21-54)
-template <int M>
-__device__ __forceinline__ bool in_mesh(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz)
+// FULL = true: the caller knows nv == M (every slot of the record is a real vertex), so the per-slot
+// `k < nv` selects and the wrap-around selects fold away at compile time -- the hexagon fast path.
+template <int M, bool FULL = false>
+__device__ __forceinline__ bool in_mesh(const CellRec<M>* __restrict__ rec, int nv_in, double px, double py, double pz)
 {
+    const int nv = FULL ? M : nv_in;
     if (!finite3(px, py, pz)) return false; // TK:29-33
     bool inside = true;
 #pragma unroll
@@ -96,10 +99,11 @@ __device__ __forceinline__ bool in_mesh(const CellRec<M>* __restrict__ rec, int 
 
 // Interpolator::CalcPolygonWachspress (src/Utils/Interpolation.hpp:137-165) with the corner areas B_i
 // taken from the record.  wfinite: all weights finite (a point exactly on an edge gives inf/NaN, N7).
-template <int M>
-__device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
+template <int M, bool FULL = false>
+__device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict__ rec, int nv_in, double px, double py, double pz,
                                                    double (&w)[M], bool& wfinite)
 {
+    const int nv = FULL ? M : nv_in;
     double ax[M], ay[M], az[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) {
@@ -150,12 +154,12 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
 }
 
 // returns false when the point is not in the cell (IsInMesh); else fills the normalised weights
-template <int M>
+template <int M, bool FULL = false>
 __device__ __forceinline__ bool cell_weights(const CellRec<M>* __restrict__ rec, int nv, double px, double py, double pz,
                                              double (&w)[M], bool& wfinite)
 {
-    if (!in_mesh<M>(rec, nv, px, py, pz)) return false;
-    wachspress_weights<M>(rec, nv, px, py, pz, w, wfinite);
+    if (!in_mesh<M, FULL>(rec, nv, px, py, pz)) return false;
+    wachspress_weights<M, FULL>(rec, nv, px, py, pz, w, wfinite);
     return true;
 }
 
@@ -167,7 +171,7 @@ struct LayerRes {
 
 // FAST PATH: the column is provably non-increasing, so raw value == fixed-up value and levels
 // are probed on the fly with the weights / row offsets held in registers.
-template <int M>
+template <int M, bool FULL = false>
 struct ZCol {
     const double* __restrict__ ztop;
     const double (&w)[M];
@@ -179,7 +183,7 @@ struct ZCol {
         double z = 0.0;
 #pragma unroll
         for (int i = 0; i < M; ++i)
-            if (i < nv) z += w[i] * ztop[vo[i] + k]; // VK:774-781, accumulated in vertex order
+            if (FULL || i < nv) z += w[i] * ztop[vo[i] + k]; // VK:774-781, accumulated in vertex order
         return z;
     }
 };
@@ -258,8 +262,8 @@ __device__ __noinline__ LayerRes slow_layer_stream(const CellRec<M>* __restrict_
 
 // `hint` (a previous answer, or < 1) is accepted only if it is the unique matching layer, in
 // which case the reference's search returns it as well (proof in DESIGN.md, "layer hint").
-template <int M>
-__device__ __forceinline__ LayerRes layer_search_stream(const ZCol<M>& z, double d, int hint)
+template <int M, bool FULL>
+__device__ __forceinline__ LayerRes layer_search_stream(const ZCol<M, FULL>& z, double d, int hint)
 {
     const double eps = 1e-8;
     const int L = z.L;
@@ -361,8 +365,8 @@ __device__ __noinline__ LayerRes slow_layer_latitude(const CellRec<M>* __restric
 }
 
 // On a non-increasing column the first match is the smallest k with d >= z[k]-eps (lower bound).
-template <int M>
-__device__ __forceinline__ LayerRes layer_search_path(const ZCol<M>& z, double d, int hint)
+template <int M, bool FULL>
+__device__ __forceinline__ LayerRes layer_search_path(const ZCol<M, FULL>& z, double d, int hint)
 {
     const double eps = 1e-8;
     const int L = z.L;
@@ -395,14 +399,14 @@ __device__ __forceinline__ LayerRes layer_search_path(const ZCol<M>& z, double d
 }
 
 // TBBKernel::CalcVelocity + CalcAttribute on the packed (vx,vy,vz,w) records, TK:128-164
-template <int M>
+template <int M, bool FULL = false>
 __device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, const int (&vo)[M], const double (&w)[M], int nv,
                                             int layer, double& x, double& y, double& z, double& ww)
 {
     x = 0.0; y = 0.0; z = 0.0; ww = 0.0;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        if (i < nv) {
+        if (FULL || i < nv) {
             const double4 v = velw[vo[i] + layer];
             x += w[i] * v.x;
             y += w[i] * v.y;
@@ -412,13 +416,13 @@ __device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, co
     }
 }
 
-template <int M>
+template <int M, bool FULL = false>
 __device__ __forceinline__ double gather_scalar(const double* __restrict__ a, const int (&vo)[M], const double (&w)[M], int nv, int layer)
 {
     double r = 0.0;
 #pragma unroll
     for (int i = 0; i < M; ++i)
-        if (i < nv) r += w[i] * a[vo[i] + layer];
+        if (FULL || i < nv) r += w[i] * a[vo[i] + layer];
     return r;
 }
 
@@ -429,21 +433,21 @@ struct EvalOut {
 };
 
 // calc_velocity_at (streamline), VK:740-872.  Returns ST_ALIVE or the reason of failure.
-template <int M>
+template <int M, bool FULL = false>
 __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, const SnapView& s, bool mono, int L,
                                            const d3& p, double depth, int& hint, EvalOut& o)
 {
-    const int nv = rec->nv;
+    const int nv = FULL ? M : rec->nv;
     if (nv <= 0) return ST_BAD_SETUP;
     double w[M];
     bool wfinite = false;
-    if (!cell_weights<M>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    if (!cell_weights<M, FULL>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
     int vo[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+    for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? rec->vid[i] * L : 0;
 
     LayerRes lr;
-    if (mono && wfinite) lr = layer_search_stream<M>(ZCol<M>{s.ztop, w, vo, nv, L}, depth, hint);
+    if (mono && wfinite) lr = layer_search_stream<M, FULL>(ZCol<M, FULL>{s.ztop, w, vo, nv, L}, depth, hint);
     else lr = slow_layer_stream<M>(rec, s.ztop, L, p.x, p.y, p.z, depth);
     const int layer = lr.layer;
     const double ztop_up = lr.top, ztop_dn = lr.bot;
@@ -456,8 +460,8 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
     const double t = (x - ztop_dn) / denom;
 
     double dx, dy, dz, dw, ux, uy, uz, uw;
-    gather_velw<M>(s.velw, vo, w, nv, layer, dx, dy, dz, dw);
-    gather_velw<M>(s.velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
+    gather_velw<M, FULL>(s.velw, vo, w, nv, layer, dx, dy, dz, dw);
+    gather_velw<M, FULL>(s.velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
     if (len3(dx, dy, dz) < 1e-12 || len3(ux, uy, uz) < 1e-12) return ST_ZERO_VELOCITY; // VK:845-847
     const double omt = 1.0 - t;
     o.hx = t * ux + omt * dx; // VK:849
@@ -473,19 +477,19 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
 // search each, shared weights), blended with alpha; no zero-velocity reject.  sv[0] = front,
 // sv[1] = back; the two snapshots go through ONE copy of the code (loops kept rolled) to
 // keep the kernel's instruction footprint down.
-template <int M>
+template <int M, bool FULL = false>
 __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv,
                                          bool mono_f, bool mono_b, int L, int attr_count, const d3& p, double depth,
                                          double alpha, int& hint_f, int& hint_b, EvalOut& o)
 {
-    const int nv = rec->nv;
+    const int nv = FULL ? M : rec->nv;
     if (nv <= 0) return ST_BAD_SETUP;
     double w[M];
     bool wfinite = false;
-    if (!cell_weights<M>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    if (!cell_weights<M, FULL>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
     int vo[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+    for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? rec->vid[i] * L : 0;
 
     // both layer searches first (VK:1182-1222) ...
     int lf = -1, lb = -1;
@@ -495,7 +499,7 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
         const bool mono = s ? mono_b : mono_f;
         const int hint = s ? hint_b : hint_f;
         LayerRes r;
-        if (mono && wfinite) r = layer_search_path<M>(ZCol<M>{sv[s].ztop, w, vo, nv, L}, depth, hint);
+        if (mono && wfinite) r = layer_search_path<M, FULL>(ZCol<M, FULL>{sv[s].ztop, w, vo, nv, L}, depth, hint);
         else r = slow_layer_path<M>(rec, sv[s].ztop, L, p.x, p.y, p.z, depth);
         if (s == 0) { lf = r.layer; f_up = r.top; f_dn = r.bot; }
         else { lb = r.layer; b_up = r.top; b_dn = r.bot; }
@@ -526,17 +530,17 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
         const double t = s ? t_back : t_front;
         const double omt = 1.0 - t;
         double dx, dy, dz, dw, ux, uy, uz, uw;
-        gather_velw<M>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw);
-        gather_velw<M>(sv[s].velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
+        gather_velw<M, FULL>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw);
+        gather_velw<M, FULL>(sv[s].velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
         const double vx = t * ux + omt * dx, vy = t * uy + omt * dy, vz = t * uz + omt * dz;
         const double vw = t * uw + omt * dw;
         double a0 = 0.0, a1 = 0.0;
         if (attr_count >= 1) {
-            const double ad = gather_scalar<M>(sv[s].attr0, vo, w, nv, layer), au = gather_scalar<M>(sv[s].attr0, vo, w, nv, layer - 1);
+            const double ad = gather_scalar<M, FULL>(sv[s].attr0, vo, w, nv, layer), au = gather_scalar<M, FULL>(sv[s].attr0, vo, w, nv, layer - 1);
             a0 = t * au + omt * ad;
         }
         if (attr_count >= 2) {
-            const double ad = gather_scalar<M>(sv[s].attr1, vo, w, nv, layer), au = gather_scalar<M>(sv[s].attr1, vo, w, nv, layer - 1);
+            const double ad = gather_scalar<M, FULL>(sv[s].attr1, vo, w, nv, layer), au = gather_scalar<M, FULL>(sv[s].attr1, vo, w, nv, layer - 1);
             a1 = t * au + omt * ad;
         }
         if (s == 0) {

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     int cand[M + 1];
 #pragma unroll
                     for (int k = 0; k < M; ++k) {
-                        cand[k] = (k < nv) ? r->nbr[k] : -1;
+                        cand[k] = r->nbr[k]; // slots >= nv hold -1 (upload_records)
                         if (cand[k] >= 0) {
                             const double4 cc = P.c4[cand[k]];
                             const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
@@ -463,8 +463,13 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                         const double a = min_edge_angle<M>(rec_s, rec_s->nv, p.x, p.y, p.z);
                         if (a < edge_min) edge_min = a;
                     }
-                    st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
-                              : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
+                    // hexagon fast path: with nv == M every per-slot select of the evaluation folds away
+                    if (M == 6 && rec_s->nv == M)
+                        st = PATH ? eval_path<M, true>(rec_s, P.sv, mf, mb, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                                  : eval_stream<M, true>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
+                    else
+                        st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                                  : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
                     if (st != ST_ALIVE) break;
                     if (s == 0) {
                         hvel = mk3(o.hx, o.hy, o.hz);
