@@ -494,10 +494,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                         double q6[6];
                         bool ok6 = true;
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) {
-                            q6[i] = div_by6(a6[i]);
-                            ok6 = ok6 && dv_num_ok(a6[i]) && dv_quo_ok(q6[i], a6[i]);
-                        }
+                        for (int i = 0; i < 6; ++i) q6[i] = div_by6(a6[i], ok6);
                         if (!ok6) {
 #pragma unroll
                             for (int i = 0; i < 6; ++i) q6[i] = slow_div(a6[i], 6.0);
