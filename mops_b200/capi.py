@@ -84,10 +84,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with mops_b200/csrc/build.sh "
+    path = os.environ.get("MOPS_B200_LIB", LIB_PATH)   # developer override: A/B runs of differently built kernels
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with mops_b200/csrc/build.sh "
                            "(or __graft_entry__.build()); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.mops_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.mops_destroy.argtypes = [vp]

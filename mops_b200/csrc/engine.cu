@@ -399,51 +399,35 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
     }
 }
 
-template <int M, int MINB>
-void launch_advect_occ(mops_ctx* ctx, const AdvectParams& P, bool path)
+// Instantiations of the advection kernel: EXTRA (walk semantics / near-edge diagnostic) and ATTR (pathline
+// scalar attributes carried along) are compile-time switches, so the production pathline without attributes
+// does not pay registers for either.  Resident 128-thread blocks per SM (register budget 65536 / (128 * MINB)):
+// 3 for the 6- and 8-wide records, 1 for the 20-wide ones -- from measurements on B200 (profiles/README.md:
+// 2 blocks 990 ms, 3 blocks 817 ms, 4 blocks 855 ms, 5 blocks 1065 ms, 6 blocks 1298 ms on the same step).
+template <int M, bool PATH, bool EXTRA, bool ATTR>
+void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 {
     const int grid = blocks_for(P.n, 128);
-    if (path) k_advect<M, true, MINB, false><<<grid, 128, 0, ctx->stream>>>(P);
-    else k_advect<M, false, MINB, false><<<grid, 128, 0, ctx->stream>>>(P);
+    k_advect<M, PATH, (M == 20 ? 1 : 3), EXTRA, ATTR><<<grid, 128, 0, ctx->stream>>>(P);
     ctx->launches++;
-}
-
-// resident 128-thread blocks per SM the advection kernel is compiled for (register budget =
-// 65536 / (128 * MINB)); chosen from measurements on B200 (profiles/), overridable for experiments
-int advect_minb()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("MOPS_ADVECT_MINB");
-        v = e ? atoi(e) : 3;
-        if (v < 2 || v > 6) v = 3;
-    }
-    return v;
 }
 
 template <int M>
 void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
-    if (P.walk || P.diag_edge) { // walk semantics / near-edge diagnostic: the EXTRA instantiation
-        const int grid = blocks_for(P.n, 128);
-        if (path) k_advect<M, true, (M == 20 ? 1 : 3), true><<<grid, 128, 0, ctx->stream>>>(P);
-        else k_advect<M, false, (M == 20 ? 1 : 3), true><<<grid, 128, 0, ctx->stream>>>(P);
-        ctx->launches++;
-        return;
-    }
-    if constexpr (M == 6) {
-        switch (advect_minb()) {
-        case 2: launch_advect_occ<M, 2>(ctx, P, path); return;
-        case 4: launch_advect_occ<M, 4>(ctx, P, path); return;
-        case 5: launch_advect_occ<M, 5>(ctx, P, path); return;
-        case 6: launch_advect_occ<M, 6>(ctx, P, path); return;
-        default: launch_advect_occ<M, 3>(ctx, P, path); return;
-        }
+    const bool extra = P.walk || P.diag_edge;
+    const bool attr = path && P.attr_count > 0 && P.out_attr;
+    if (!path) {
+        if (extra) launch_advect_inst<M, false, true, false>(ctx, P);
+        else launch_advect_inst<M, false, false, false>(ctx, P);
+    } else if (attr) {
+        if (extra) launch_advect_inst<M, true, true, true>(ctx, P);
+        else launch_advect_inst<M, true, false, true>(ctx, P);
     } else {
-        launch_advect_occ<M, (M == 8 ? 3 : 1)>(ctx, P, path);
+        if (extra) launch_advect_inst<M, true, true, false>(ctx, P);
+        else launch_advect_inst<M, true, false, false>(ctx, P);
     }
 }
-
 
 // one particle range on the device: start cells (given or located) -> Morton order -> advection kernel, all on
 // ctx->stream.  `S` supplies the sort scratch; P carries the device pointers of the range.

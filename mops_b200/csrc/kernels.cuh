@@ -356,7 +356,9 @@ __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : (
 // EXTRA = false is the production instantiation; EXTRA = true additionally honours P.walk
 // (MOPS_SEM_WALK) and P.diag_edge (near-edge counting) -- kept out of the hot variant because even
 // never-taken branches cost registers and ~4 % of the kernel time here.
-template <int M, bool PATH, int MINB, bool EXTRA>
+// ATTR = true carries the pathline's scalar attributes (P.attr_count > 0 and an output buffer); without it the
+// attribute accumulators do not exist.
+template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR>
 __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
 {
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     for (int k = 0; k < M; ++k) {
                         cand[k] = r->nbr[k]; // slots >= nv hold -1 (upload_records)
                         if (cand[k] >= 0) {
-                            const double4 cc = P.c4[cand[k]];
+                            const double4 cc = ldg_d4(P.c4 + cand[k]);
                             const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
                             len[k] = dx * dx + dy * dy + dz * dz;
                         } else {
@@ -411,15 +413,29 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                         }
                     }
                     {
-                        const double4 cc = P.c4[cell];
+                        const double4 cc = ldg_d4(P.c4 + cell);
                         const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
                         len[M] = dx * dx + dy * dy + dz * dz;
                         cand[M] = cell;
                     }
-                    sqrt_group<M + 1>(len);
+                    // argmin on the squared distances; sqrt is monotone, so the sqrt'd compare of the reference can
+                    // only differ when two candidates round to the same root, i.e. lie within a few ulp of each
+                    // other -- then (and only then) the roots are taken and compared as the reference does
+                    double m1 = 1.7976931348623157e308;
 #pragma unroll
                     for (int k = 0; k <= M; ++k)
-                        if (cand[k] >= 0 && len[k] < min_len) { min_len = len[k]; best = cand[k]; }
+                        if (cand[k] >= 0 && len[k] < m1) { m1 = len[k]; best = cand[k]; }
+                    const double lim = m1 + m1 * 0x1p-48;
+                    int close = 0;
+#pragma unroll
+                    for (int k = 0; k <= M; ++k) close += (cand[k] >= 0 && len[k] <= lim) ? 1 : 0;
+                    if (close > 1 || !(m1 < 1.0e300)) {
+                        best = cell;
+                        sqrt_group<M + 1>(len);
+#pragma unroll
+                        for (int k = 0; k <= M; ++k)
+                            if (cand[k] >= 0 && len[k] < min_len) { min_len = len[k]; best = cand[k]; }
+                    }
                     if (best != cell) { cell = best; }
                     // walk mode: not limited to one ring (identical whenever the step is shorter than a cell)
                     if (EXTRA && P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
@@ -448,7 +464,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     d3 p = pos;
                     double a_s = alpha;
                     if (s > 0) {
-                        p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5);
+                        p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5, r);
                         if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
                     }
                     const CellRec<M>* __restrict__ rec_s = rec;
@@ -465,23 +481,26 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     }
                     // hexagon fast path: with nv == M every per-slot select of the evaluation folds away
                     if (M == 6 && rec_s->nv == M)
-                        st = PATH ? eval_path<M, true>(rec_s, P.sv, mf, mb, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                        st = PATH ? eval_path<M, true>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
                                   : eval_stream<M, true>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
                     else
-                        st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, P.attr_count, p, cur_depth, a_s, hint_f, hint_b, o)
+                        st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
                                   : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
                     if (st != ST_ALIVE) break;
                     if (s == 0) {
                         hvel = mk3(o.hx, o.hy, o.hz);
-                        vvel = o.vv; at0 = o.a0; at1 = o.a1;
+                        vvel = o.vv;
+                        if (ATTR) { at0 = o.a0; at1 = o.a1; }
                     } else {
                         const double c = (s == 3) ? 1.0 : 2.0; // s1 + 2 s2 + 2 s3 + s4, left to right (VK:959-960)
                         hvel.x = hvel.x + c * o.hx;
                         hvel.y = hvel.y + c * o.hy;
                         hvel.z = hvel.z + c * o.hz;
                         vvel = vvel + c * o.vv;
-                        at0 = at0 + c * o.a0;
-                        at1 = at1 + c * o.a1;
+                        if (ATTR) {
+                            at0 = at0 + c * o.a0;
+                            at1 = at1 + c * o.a1;
+                        }
                     }
                     hprev = mk3(o.hx, o.hy, o.hz);
                 }
@@ -517,7 +536,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                 if (first_vel) { // VK:988-991 / VK:1449-1456
                     first_vel = false;
                     st3(P.out_vel, base, hvel.x, hvel.y, hvel.z);
-                    if (PATH && P.attr_count > 0 && P.out_attr) st3(P.out_attr, base, at0, at1, 0.0);
+                    if (ATTR) st3(P.out_attr, base, at0, at1, 0.0);
                 }
 
                 // depth / radius update with the float round trip (VK:977-986, R3, R4)
@@ -542,7 +561,7 @@ __global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
                     if (upd < P.each) {
                         st3(P.out_pos, base + upd, pos.x, pos.y, pos.z);
                         st3(P.out_vel, base + upd, hvel.x, hvel.y, hvel.z);
-                        if (PATH && P.attr_count > 0 && P.out_attr) st3(P.out_attr, base + upd, at0, at1, 0.0);
+                        if (ATTR) st3(P.out_attr, base + upd, at0, at1, 0.0);
                     }
                     ++upd;
                 }
