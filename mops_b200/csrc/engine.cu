@@ -407,8 +407,8 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
 template <int M, bool PATH, bool EXTRA, bool ATTR>
 void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 {
-    const int grid = blocks_for(P.n, 128);
-    k_advect<M, PATH, (M == 20 ? 1 : 3), EXTRA, ATTR><<<grid, 128, 0, ctx->stream>>>(P);
+    const int grid = blocks_for(P.n, MOPS_ADV_BLOCK);
+    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
     ctx->launches++;
 }
 

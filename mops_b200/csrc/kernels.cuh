@@ -358,8 +358,16 @@ __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : (
 // never-taken branches cost registers and ~4 % of the kernel time here.
 // ATTR = true carries the pathline's scalar attributes (P.attr_count > 0 and an output buffer); without it the
 // attribute accumulators do not exist.
+// Block size / resident blocks of the advection kernel: build-time knobs so occupancy variants can be A/B'd
+// (scripts/gpu_ab.sh); the defaults are the measured best on B200.
+#ifndef MOPS_ADV_BLOCK
+#define MOPS_ADV_BLOCK 128
+#endif
+#ifndef MOPS_ADV_MINB
+#define MOPS_ADV_MINB 3
+#endif
 template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR>
-__global__ void __launch_bounds__(128, MINB) k_advect(const AdvectParams P)
+__global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectParams P)
 {
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0, my_alive = 0, my_near = 0;
