@@ -28,6 +28,13 @@
 
 namespace mops {
 
+// row offset (vertex id * L) into the vertex-major snapshot arrays: unsigned, so address arithmetic needs no sign word
+typedef unsigned voff_t;
+
+#ifndef MOPS_UNROLL_SNAP
+#define MOPS_UNROLL_SNAP 0
+#endif
+
 // ---- resident mesh ----------------------------------------------------------------------
 template <int M>
 struct alignas(32) CellRec {
@@ -175,7 +182,7 @@ template <int M, bool FULL = false>
 struct ZCol {
     const double* __restrict__ ztop;
     const double (&w)[M];
-    const int (&vo)[M];
+    const voff_t (&vo)[M];
     int nv;
     int L;
     __device__ __forceinline__ double operator()(int k) const
@@ -185,6 +192,20 @@ struct ZCol {
         for (int i = 0; i < M; ++i)
             if (FULL || i < nv) z += w[i] * ztop[vo[i] + k]; // VK:774-781, accumulated in vertex order
         return z;
+    }
+    // z(k-1) and z(k) in one pass: one row pointer per vertex, the upper level at a fixed -8 B offset (each
+    // accumulator still sums in vertex order, so both values are bit-equal to operator())
+    __device__ __forceinline__ void pair(int k, double& top, double& bot) const
+    {
+        top = 0.0; bot = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            if (FULL || i < nv) {
+                const double* __restrict__ q = ztop + (vo[i] + (voff_t)k);
+                top += w[i] * q[-1];
+                bot += w[i] * q[0];
+            }
+        }
     }
 };
 
@@ -241,14 +262,14 @@ __device__ __forceinline__ LayerRes binary_layer_search(const Z& z, int L, doubl
     }
     LayerRes r;
     r.layer = layer;
-    r.top = z(layer - 1);
-    r.bot = z(layer);
+    z.pair(layer, r.top, r.bot);
     return r;
 }
 
 struct ArrayCol {
     const double* col;
     __device__ __forceinline__ double operator()(int k) const { return col[k]; }
+    __device__ __forceinline__ void pair(int k, double& top, double& bot) const { top = col[k - 1]; bot = col[k]; }
 };
 
 template <int M>
@@ -270,8 +291,7 @@ __device__ __forceinline__ LayerRes layer_search_stream(const ZCol<M, FULL>& z, 
     if (hint >= 1 && hint <= L - 1) {
         LayerRes r;
         r.layer = hint;
-        r.top = z(hint - 1);
-        r.bot = z(hint);
+        z.pair(hint, r.top, r.bot);
         if (d <= r.top + eps && d >= r.bot - eps && d > r.bot + eps && d < r.top - eps) return r;
     }
     return binary_layer_search(z, L, d);
@@ -373,8 +393,7 @@ __device__ __forceinline__ LayerRes layer_search_path(const ZCol<M, FULL>& z, do
     LayerRes r;
     if (hint >= 1 && hint <= L - 1) {
         r.layer = hint;
-        r.top = z(hint - 1);
-        r.bot = z(hint);
+        z.pair(hint, r.top, r.bot);
         // hint is the first match iff it matches and hint-1 does not (or hint == 1)
         if (d >= r.bot - eps && d <= r.top + eps && (hint == 1 ? true : (d < r.top - eps))) return r;
     }
@@ -393,14 +412,13 @@ __device__ __forceinline__ LayerRes layer_search_path(const ZCol<M, FULL>& z, do
         layer = lo;
     }
     r.layer = layer;
-    r.top = z(layer - 1);
-    r.bot = z(layer);
+    z.pair(layer, r.top, r.bot);
     return r;
 }
 
 // TBBKernel::CalcVelocity + CalcAttribute on the packed (vx,vy,vz,w) records, TK:128-164
 template <int M, bool FULL = false>
-__device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, const int (&vo)[M], const double (&w)[M], int nv,
+__device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, const voff_t (&vo)[M], const double (&w)[M], int nv,
                                             int layer, double& x, double& y, double& z, double& ww)
 {
     x = 0.0; y = 0.0; z = 0.0; ww = 0.0;
@@ -416,8 +434,36 @@ __device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, co
     }
 }
 
+// levels `layer` (d*) and `layer - 1` (u*) of one snapshot in one pass over the vertices: one record pointer per
+// vertex, the upper level at a fixed -32 B offset.  Every accumulator sums in vertex order exactly as
+// gather_velw does, so the results are bit-equal to two gather_velw calls.
 template <int M, bool FULL = false>
-__device__ __forceinline__ double gather_scalar(const double* __restrict__ a, const int (&vo)[M], const double (&w)[M], int nv, int layer)
+__device__ __forceinline__ void gather_velw_pair(const double4* __restrict__ velw, const voff_t (&vo)[M], const double (&w)[M], int nv,
+                                                 int layer, double& dx, double& dy, double& dz, double& dw,
+                                                 double& ux, double& uy, double& uz, double& uw)
+{
+    dx = 0.0; dy = 0.0; dz = 0.0; dw = 0.0;
+    ux = 0.0; uy = 0.0; uz = 0.0; uw = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        if (FULL || i < nv) {
+            const double4* __restrict__ q = velw + (vo[i] + (voff_t)layer); // nV * L < 2^32 (checked at upload)
+            const double4 d = ldg_d4(q);
+            const double4 u = ldg_d4(q - 1);
+            dx += w[i] * d.x;
+            dy += w[i] * d.y;
+            dz += w[i] * d.z;
+            dw += w[i] * d.w;
+            ux += w[i] * u.x;
+            uy += w[i] * u.y;
+            uz += w[i] * u.z;
+            uw += w[i] * u.w;
+        }
+    }
+}
+
+template <int M, bool FULL = false>
+__device__ __forceinline__ double gather_scalar(const double* __restrict__ a, const voff_t (&vo)[M], const double (&w)[M], int nv, int layer)
 {
     double r = 0.0;
 #pragma unroll
@@ -442,9 +488,9 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
     double w[M];
     bool wfinite = false;
     if (!cell_weights<M, FULL>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
-    int vo[M];
+    voff_t vo[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? rec->vid[i] * L : 0;
+    for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? (voff_t)rec->vid[i] * (voff_t)L : 0u;
 
     LayerRes lr;
     if (mono && wfinite) lr = layer_search_stream<M, FULL>(ZCol<M, FULL>{s.ztop, w, vo, nv, L}, depth, hint);
@@ -460,8 +506,7 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
     const double t = (x - ztop_dn) / denom;
 
     double dx, dy, dz, dw, ux, uy, uz, uw;
-    gather_velw<M, FULL>(s.velw, vo, w, nv, layer, dx, dy, dz, dw);
-    gather_velw<M, FULL>(s.velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
+    gather_velw_pair<M, FULL>(s.velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
     if (len3(dx, dy, dz) < 1e-12 || len3(ux, uy, uz) < 1e-12) return ST_ZERO_VELOCITY; // VK:845-847
     const double omt = 1.0 - t;
     o.hx = t * ux + omt * dx; // VK:849
@@ -487,14 +532,16 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
     double w[M];
     bool wfinite = false;
     if (!cell_weights<M, FULL>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
-    int vo[M];
+    voff_t vo[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? rec->vid[i] * L : 0;
+    for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? (voff_t)rec->vid[i] * (voff_t)L : 0u;
 
     // both layer searches first (VK:1182-1222) ...
     int lf = -1, lb = -1;
     double f_up = 0.0, f_dn = 0.0, b_up = 0.0, b_dn = 0.0;
-#pragma unroll 1
+    // front/back through one rolled copy of the code by default; MOPS_UNROLL_SNAP=1 unrolls the hexagon fast path
+    constexpr int US = (FULL && MOPS_UNROLL_SNAP) ? 2 : 1;
+#pragma unroll US
     for (int s = 0; s < 2; ++s) {
         const bool mono = s ? mono_b : mono_f;
         const int hint = s ? hint_b : hint_f;
@@ -527,14 +574,13 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
     // ... then the gathers and the alpha blend (VK:1243-1324)
     const double oma = 1.0 - alpha;
     double ffx = 0.0, ffy = 0.0, ffz = 0.0, ffw = 0.0, fa0 = 0.0, fa1 = 0.0;
-#pragma unroll 1
+#pragma unroll US
     for (int s = 0; s < 2; ++s) {
         const int layer = s ? lb : lf;
         const double t = s ? t_back : t_front;
         const double omt = 1.0 - t;
         double dx, dy, dz, dw, ux, uy, uz, uw;
-        gather_velw<M, FULL>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw);
-        gather_velw<M, FULL>(sv[s].velw, vo, w, nv, layer - 1, ux, uy, uz, uw);
+        gather_velw_pair<M, FULL>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
         const double vx = t * ux + omt * dx, vy = t * uy + omt * dy, vz = t * uz + omt * dz;
         const double vw = t * uw + omt * dw;
         double a0 = 0.0, a1 = 0.0;

@@ -675,9 +675,9 @@ __global__ void __launch_bounds__(128) k_remap(const RemapParams P)
         bool wfinite = false;
         ok = (nv > 0) && cell_weights<M>(rec, nv, pos.x, pos.y, pos.z, w, wfinite);
         if (ok) {
-            int vo[M];
+            voff_t vo[M];
 #pragma unroll
-            for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+            for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? (voff_t)rec->vid[i] * (voff_t)L : 0u;
             const double DEPTH = P.DEPTH;
             int local_layer = -1;
             double topI = 0.0, botI = 0.0;
@@ -847,9 +847,9 @@ __global__ void __launch_bounds__(128) k_view(const ViewParams P)
             double w[M];
             bool wfinite = false;
             wachspress_weights<M>(rec, nv, pos.x, pos.y, pos.z, w, wfinite);
-            int vo[M];
+            voff_t vo[M];
 #pragma unroll
-            for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? rec->vid[i] * L : 0;
+            for (int i = 0; i < M; ++i) vo[i] = (i < nv) ? (voff_t)rec->vid[i] * (voff_t)L : 0u;
             double dummy;
             if (MODE == 0) {
                 gather_velw<M>(P.s.velw, vo, w, nv, P.fixed_layer, fx, fy, fz, dummy); // VK:220-226
