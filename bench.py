@@ -410,7 +410,12 @@ def main():
                 "traffic": traffic, "kernel": "k_advect<6,true>", "peak_source": peak_src,
                 "algorithmic_bytes_per_particle_step": bps, "kernel_ms_per_launch": float(np.mean(kms)),
                 "kernel_share_of_step": float(np.sum(kms)) / (ev0.elapsed_time(ev1) if world == 1 else ms_total),
-                "note": "logical bytes ignore L1/L2 reuse between particles sharing a cell; frac > 1 would mean cache-bound"}
+                "note": "logical bytes ignore L1/L2 reuse between particles sharing a cell; frac > 1 means the kernel is "
+                        "cache-/fp64-bound, not HBM-bound (profiles/README.md): dram_* is the real DRAM rate"}
+    if traffic and world == 1 and args.level == 9 and args.particles == 64_000_000 and args.interval_steps == 120 and kms:
+        # traffic.json is an ncu capture of exactly this launch shape (64 M particles x 120 steps, level-9 mesh)
+        roofline["dram_achieved"] = float(traffic) / (float(np.mean(kms)) / 1e3) / 1e9
+        roofline["dram_frac"] = roofline["dram_achieved"] / peak
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
