@@ -183,6 +183,10 @@ typedef struct mops_traj_stats {
     int64_t near_edge_particles; /* particles that came within 1e-12 rad of a cell edge (count_near_edge) */
 } mops_traj_stats;
 
+/* Both calls integrate in launches of 40 steps (environment MOPS_SEGMENT_STEPS=<n>, 0 = one launch) with the
+ * particles that stopped compacted away between launches -- results are identical either way.  Between launches the
+ * host reads back the live count, so a call with more steps than one launch has synchronised with the stream before
+ * it returns; calls that fit one launch and pass stats = NULL stay asynchronous with MOPS_MEM_DEVICE buffers. */
 /* replaces MOPS::Factory::StreamLine (src/Common/MOPSFactory.h:28-33 -> VK:653-1015) */
 int mops_streamline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io,
                     mops_traj_stats* stats);

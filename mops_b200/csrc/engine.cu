@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +75,9 @@ struct mops_ctx {
     // particle scratch (host-memory mode) + sort scratch
     Buf p_xyz, p_depth, p_cell0, p_cell_int, p_out_pos, p_out_vel, p_out_attr, p_log, p_status, p_steps, p_fcell, p_edge;
     Buf s_keys, s_vals, s_keys2, s_vals2, s_tmp;
+    Buf s_state;            // AdvState[n]: parked loop state of the compacting multi-launch form
+    int* d_nsel = nullptr;  // number of live particles after a compaction
+    int segment_steps = 40; // steps per launch of the compacting form; MOPS_SEGMENT_STEPS overrides (0 = one launch per call)
     Buf r_img0, r_img1, r_cells;
     unsigned long long* counters = nullptr; // [4]
     // HOST-mode pipeline (large n): two sets of chunk-sized scratch so that the H2D of chunk k+1 and the D2H
@@ -404,28 +408,41 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
 // does not pay registers for either.  Resident 128-thread blocks per SM (register budget 65536 / (128 * MINB)):
 // 3 for the 6- and 8-wide records, 1 for the 20-wide ones -- from measurements on B200 (profiles/README.md:
 // 2 blocks 990 ms, 3 blocks 817 ms, 4 blocks 855 ms, 5 blocks 1065 ms, 6 blocks 1298 ms on the same step).
-template <int M, bool PATH, bool EXTRA, bool ATTR>
+template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false>
 void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 {
     const int grid = blocks_for(P.n, MOPS_ADV_BLOCK);
-    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
+    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR, SEG><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
     ctx->launches++;
 }
 
+// seg = true: a segment of a compacting multi-launch call (never combined with the EXTRA instantiations)
 template <int M>
-void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
+void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool seg = false)
 {
     const bool extra = P.walk || P.diag_edge;
     const bool attr = path && P.attr_count > 0 && P.out_attr;
     if (!path) {
         if (extra) launch_advect_inst<M, false, true, false>(ctx, P);
+        else if (seg) launch_advect_inst<M, false, false, false, true>(ctx, P);
         else launch_advect_inst<M, false, false, false>(ctx, P);
     } else if (attr) {
         if (extra) launch_advect_inst<M, true, true, true>(ctx, P);
+        else if (seg) launch_advect_inst<M, true, false, true, true>(ctx, P);
         else launch_advect_inst<M, true, false, true>(ctx, P);
     } else {
         if (extra) launch_advect_inst<M, true, true, false>(ctx, P);
+        else if (seg) launch_advect_inst<M, true, false, false, true>(ctx, P);
         else launch_advect_inst<M, true, false, false>(ctx, P);
+    }
+}
+
+void dispatch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool seg)
+{
+    switch (ctx->M) {
+    case 6: launch_advect<6>(ctx, P, path, seg); break;
+    case 8: launch_advect<8>(ctx, P, path, seg); break;
+    default: launch_advect<20>(ctx, P, path, seg); break;
     }
 }
 
@@ -462,13 +479,49 @@ int run_range(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, long long m, c
         d_order = (const int*)vals2.p;
     }
     P.n = m; P.order = d_order; P.cell0 = d_cell_int;
+    P.step_begin = 0; P.step_end = P.times; P.state = nullptr;
     if (ev_k0) CK(cudaEventRecord(ev_k0, st));
-    switch (ctx->M) {
-    case 6: launch_advect<6>(ctx, P, path); break;
-    case 8: launch_advect<8>(ctx, P, path); break;
-    default: launch_advect<20>(ctx, P, path); break;
+    const int seg = ctx->segment_steps;
+    if (seg > 0 && P.times > seg && !(P.walk || P.diag_edge)) {
+        // Compacting multi-launch form (default 40 steps per launch, MOPS_SEGMENT_STEPS=<steps>, 0 = off): under the reference's semantics particles
+        // stop for good at their first failed stage, and a stopped particle's lane idles until its whole warp is
+        // done.  Each launch integrates `seg` steps; particles still alive park their loop state, the processing
+        // order is compacted to them (order-preserving, so the Morton locality stays) and the next launch carries
+        // only live lanes.  Results are identical to the single launch: same per-particle arithmetic, and every
+        // output slot is still written exactly once by the launch in which the particle stops or finishes.
+        if ((rc = ensure(ctx, ctx->s_state, (size_t)m * sizeof(AdvState)))) return rc;
+        if ((rc = ensure(ctx, vals, (size_t)m * 4))) return rc;
+        if ((rc = ensure(ctx, vals2, (size_t)m * 4))) return rc;
+        int* cur = (int*)vals2.p; // the sorted order lives here
+        int* nxt = (int*)vals.p;
+        if (!d_order) { // unsorted call: start from the identity order
+            k_iota<<<blocks_for(m, 256), 256, 0, st>>>(cur, m);
+            ctx->launches++;
+        }
+        P.state = (AdvState*)ctx->s_state.p;
+        long long live = m;
+        for (int b = 0; b < P.times && live > 0; b += seg) {
+            const int e = std::min(P.times, b + seg);
+            P.n = live; P.order = cur; P.step_begin = b; P.step_end = e;
+            dispatch_advect(ctx, P, path, true);
+            CK(cudaGetLastError());
+            if (e < P.times) {
+                size_t tmp_bytes = 0;
+                const AdvAliveOp op{P.state};
+                cub::DeviceSelect::If(nullptr, tmp_bytes, (const int*)cur, nxt, ctx->d_nsel, (int)live, op, st);
+                if ((rc = ensure(ctx, tmp, tmp_bytes))) return rc;
+                CK(cub::DeviceSelect::If(tmp.p, tmp_bytes, (const int*)cur, nxt, ctx->d_nsel, (int)live, op, st));
+                int h_live = 0;
+                CK(cudaMemcpyAsync(&h_live, ctx->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                live = h_live;
+                std::swap(cur, nxt);
+            }
+        }
+    } else {
+        dispatch_advect(ctx, P, path, false);
+        CK(cudaGetLastError());
     }
-    CK(cudaGetLastError());
     if (ev_k1) CK(cudaEventRecord(ev_k1, st));
     return MOPS_OK;
 }
@@ -871,7 +924,9 @@ int mops_create(mops_ctx** out, int device_ordinal)
               cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_kend) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess &&
               cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess;
+              cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_nsel, sizeof(int)) == cudaSuccess;
+    if (const char* e = getenv("MOPS_SEGMENT_STEPS")) ctx->segment_steps = std::max(0, atoi(e));
     ctx->stream = ctx->own_stream;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -905,7 +960,7 @@ void mops_destroy(mops_ctx* ctx)
     Buf* bufs[] = {&ctx->st_zonal, &ctx->st_merid, &ctx->st_thick, &ctx->st_wtop, &ctx->st_bottom, &ctx->st_ztopc, &ctx->st_attr,
                    &ctx->st_vmono, &ctx->p_xyz, &ctx->p_depth, &ctx->p_cell0, &ctx->p_cell_int, &ctx->p_out_pos, &ctx->p_out_vel,
                    &ctx->p_out_attr, &ctx->p_log, &ctx->p_status, &ctx->p_steps, &ctx->p_fcell, &ctx->p_edge, &ctx->s_keys, &ctx->s_vals,
-                   &ctx->s_keys2, &ctx->s_vals2, &ctx->s_tmp, &ctx->r_img0, &ctx->r_img1, &ctx->r_cells};
+                   &ctx->s_keys2, &ctx->s_vals2, &ctx->s_tmp, &ctx->s_state, &ctx->r_img0, &ctx->r_img1, &ctx->r_cells};
     for (Buf* b : bufs) cudaFree(b->p);
     for (auto& ps : ctx->pipe) {
         Buf* pb[] = {&ps.xyz, &ps.depth, &ps.cell0, &ps.cell_int, &ps.vals, &ps.vals2, &ps.keys2, &ps.tmp, &ps.out_pos, &ps.out_vel,
@@ -920,6 +975,7 @@ void mops_destroy(mops_ctx* ctx)
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     cudaFree(ctx->counters);
     cudaFree(ctx->d_nonmono);
+    cudaFree(ctx->d_nsel);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
     cudaEventDestroy(ctx->ev_kend); cudaEventDestroy(ctx->ev_end);
     for (auto& m : ctx->marks) if (m) cudaEventDestroy(m);

@@ -344,6 +344,23 @@ struct AdvectParams {
     int diag_edge;    // 1 = track the smallest edge distance of every evaluated point
     int walk;         // 1 = MOPS_SEM_WALK: evaluate each stage point in the cell that contains it
     unsigned long long* counters; // [0] particle-steps started, [1] alive at end, [3] near-edge particles
+    // segmented launches (SEG instantiations only): one launch integrates steps [step_begin, step_end) of the call;
+    // particles still alive at step_end < times park their loop state in `state`, and the host compacts `order`
+    // to the live ones before the next segment, so lanes of stopped particles do not ride along to the end.
+    int step_begin, step_end;
+    struct AdvState* state; // [n], indexed by particle
+};
+
+struct alignas(32) AdvState {
+    int cell, upd, started, hint_f, hint_b;
+    int first_vel;
+    int alive; // 1 = parked, to be resumed by the next segment
+    int pad;
+};
+
+struct AdvAliveOp { // cub::DeviceSelect::If predicate over particle indices
+    const AdvState* state;
+    __device__ __forceinline__ bool operator()(const int pid) const { return state[pid].alive != 0; }
 };
 
 __device__ __forceinline__ void st3(double* p, long long i, double x, double y, double z)
@@ -366,7 +383,9 @@ __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : (
 #ifndef MOPS_ADV_MINB
 #define MOPS_ADV_MINB 3
 #endif
-template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR>
+// SEG = true: the launch covers steps [P.step_begin, P.step_end) only (see AdvectParams::state); SEG = false is the
+// single-launch kernel (every SEG-only branch folds away at compile time).
+template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR, bool SEG = false>
 __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectParams P)
 {
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,6 +406,16 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
         int hint_f = -1, hint_b = -1;
         bool first_vel = true;
         double edge_min = 1.0e300;
+        const int step_lo = SEG ? P.step_begin : 0;
+        const int step_hi = SEG ? P.step_end : P.times;
+        const bool resume = SEG && step_lo > 0;
+        if (resume) { // pick up where the previous segment parked this particle (it was alive and in a valid cell)
+            const AdvState sv = P.state[pid];
+            cell = sv.cell; upd = sv.upd; started = sv.started; hint_f = sv.hint_f; hint_b = sv.hint_b;
+            first_vel = sv.first_vel != 0;
+            run_time = step_lo * abs(P.delta_t);
+        }
+        const int started0 = started;
 
         // Every output slot is written exactly once by this thread (no host-side memset of the buffers,
         // which may be pinned host memory written over PCIe): the reference's buffers are
@@ -395,10 +424,12 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
         if (cell < 0 || cell >= P.nC) {
             status = ST_BAD_CELL; // VK:895-897: nothing is written, not even the seed
         } else {
-            st3(P.out_pos, base, pos.x, pos.y, pos.z); // VK:901
-            st3(P.out_vel, base, 0.0, 0.0, 0.0);       // overwritten by the first completed step (VK:988-991)
-            if (P.out_attr) st3(P.out_attr, base, 0.0, 0.0, 0.0);
-            for (int step = 0; step < P.times; ++step) {
+            if (!resume) {
+                st3(P.out_pos, base, pos.x, pos.y, pos.z); // VK:901
+                st3(P.out_vel, base, 0.0, 0.0, 0.0);       // overwritten by the first completed step (VK:988-991)
+                if (P.out_attr) st3(P.out_attr, base, 0.0, 0.0, 0.0);
+            }
+            for (int step = step_lo; step < step_hi; ++step) {
                 run_time += abs(P.delta_t);
                 if (step > 0) {
                     // relocation: argmin over {cellsOnCell[c][0..nv-1], c} of |centre - x|, strict <,
@@ -575,24 +606,31 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                 }
             }
         }
-        {
+        (void)has_attr_out;
+        P.pos[3 * pid] = pos.x; P.pos[3 * pid + 1] = pos.y; P.pos[3 * pid + 2] = pos.z;
+        P.depth[pid] = depth_f;
+        const bool park = SEG && status == ST_ALIVE && step_hi < P.times;
+        if (park) { // alive with steps left: the next segment resumes from here
+            AdvState sv;
+            sv.cell = cell; sv.upd = upd; sv.started = started; sv.hint_f = hint_f; sv.hint_b = hint_b;
+            sv.first_vel = first_vel ? 1 : 0; sv.alive = 1; sv.pad = 0;
+            P.state[pid] = sv;
+        } else {
             int k0 = (status == ST_BAD_CELL) ? 0 : ((upd < 1) ? 1 : ((upd < P.each) ? upd : P.each));
             for (int k = k0; k < P.each; ++k) {
                 st3(P.out_pos, base + k, 0.0, 0.0, 0.0);
                 st3(P.out_vel, base + k, 0.0, 0.0, 0.0);
                 if (P.out_attr) st3(P.out_attr, base + k, 0.0, 0.0, 0.0);
             }
+            if (SEG) P.state[pid].alive = 0;
+            if (P.status) P.status[pid] = status;
+            if (P.steps) P.steps[pid] = started;
+            if (P.fcell) P.fcell[pid] = (cell >= 0 && cell < P.nC) ? P.c_int2ext[cell] : -1;
+            if (EXTRA && P.min_edge) P.min_edge[pid] = edge_min;
+            my_alive = (status == ST_ALIVE) ? 1ull : 0ull;
+            my_near = (EXTRA && P.diag_edge && edge_min < 1e-12) ? 1ull : 0ull;
         }
-        (void)has_attr_out;
-        P.pos[3 * pid] = pos.x; P.pos[3 * pid + 1] = pos.y; P.pos[3 * pid + 2] = pos.z;
-        P.depth[pid] = depth_f;
-        if (P.status) P.status[pid] = status;
-        if (P.steps) P.steps[pid] = started;
-        if (P.fcell) P.fcell[pid] = (cell >= 0 && cell < P.nC) ? P.c_int2ext[cell] : -1;
-        if (EXTRA && P.min_edge) P.min_edge[pid] = edge_min;
-        my_steps = (unsigned long long)started;
-        my_alive = (status == ST_ALIVE) ? 1ull : 0ull;
-        my_near = (EXTRA && P.diag_edge && edge_min < 1e-12) ? 1ull : 0ull;
+        my_steps = (unsigned long long)(started - started0);
     }
     // one atomic pair per warp
 #pragma unroll
