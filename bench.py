@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--snapshot-allgather", action="store_true",
+                    help="N > 1: every rank uploads 1/N of the next snapshot over PCIe and an NCCL all-gather over NVLink "
+                         "completes it on every GPU (default: every rank uploads the whole snapshot itself)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,7 +261,39 @@ def main():
     ring = [make_snapshot_host(mesh, L, 0.02 * (1 + 0.5 * math.sin(2 * math.pi * s / 30)), 0.3 + 0.01 * s, pinned)
             for s in range(ring_n)]
 
+    # N > 1, opt-in: partitioned upload + all-gather (SURVEY 8e "broadcast of each new snapshot").  Each rank keeps only its
+    # 1/N chunk of the concatenated cell-major fields in pinned memory; the chunk goes over this rank's PCIe link on a
+    # private torch stream, an all-gather on a private NCCL communicator assembles the snapshot in HBM (double-buffered:
+    # the engine's side stream copies out of it asynchronously), and the engine takes DEVICE pointers.
+    use_ag = bool(args.snapshot_allgather) and world > 1
+    if use_ag:
+        from mops_b200 import sharding as _sh
+        nfield = mesh.n_cells * L
+        ag_total = 3 * nfield + mesh.n_cells
+        ag_chunk, _, _ = _sh.snapshot_part_bounds(ag_total, rank, world)
+        ring_parts = []
+        for h in ring:
+            part_h = pinned((ag_chunk,))
+            _sh.pack_snapshot_part([h["zonal"], h["merid"], h["thick"], h["bottom"]], rank, world, out=part_h)
+            ring_parts.append(torch.from_numpy(part_h))
+        ring = None  # the whole-snapshot host copies are not needed in this mode
+        ag_group = dist.new_group(backend="nccl")
+        ag_stream = torch.cuda.Stream()
+        ag_full = [torch.empty(ag_chunk * world, dtype=torch.float64, device=dev) for _ in range(2)]
+        ag_part = torch.empty(ag_chunk, dtype=torch.float64, device=dev)
+        ag_event = [torch.cuda.Event() for _ in range(2)]
+
     def upload(slot, s, async_):
+        if use_ag:
+            k = s % 2
+            with torch.cuda.stream(ag_stream):
+                ag_part.copy_(ring_parts[s % ring_n], non_blocking=True)
+                dist.all_gather_into_tensor(ag_full[k], ag_part, group=ag_group)
+                ag_event[k].record(ag_stream)
+            eng.side_wait_event(ag_event[k].cuda_event)
+            base = ag_full[k].data_ptr()
+            eng.set_snapshot_raw(slot, L, base, base + 8 * nfield, base + 16 * nfield, base + 24 * nfield, None, async_=async_)
+            return
         h = ring[s % ring_n]
         eng.set_snapshot_raw(slot, L, h["zonal"].ctypes.data, h["merid"].ctypes.data, h["thick"].ctypes.data,
                              h["bottom"].ctypes.data, None, async_=async_)
@@ -438,7 +473,9 @@ def main():
                            "semantics": "reference (RK4 stages in the start-of-step cell; particles stop at their first failed stage)",
                            "sorted_particles": not args.no_sort, "setup_seconds": setup_s,
                            "mesh_bytes": int(info.mesh_bytes), "snapshot_bytes": int(info.snapshot_bytes[0]),
-                           "parallelism": f"particles sharded by longitude sector over {world} GPU(s), mesh+snapshots replicated"},
+                           "parallelism": f"particles sharded by longitude sector over {world} GPU(s), mesh+snapshots replicated",
+                           "snapshot_distribution": ("1/N PCIe upload per rank + NCCL all-gather" if use_ag
+                                                     else "whole snapshot uploaded by every rank")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu

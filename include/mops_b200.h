@@ -129,6 +129,12 @@ int mops_set_snapshot_async(mops_ctx* ctx, int32_t slot, int32_t n_levels,
                             const double* bottom_depth, const double* vert_vel_top,
                             int32_t n_attr, const double* const* attrs, int32_t n_attr_total);
 int mops_snapshot_wait(mops_ctx* ctx, int32_t slot);
+/* The field pointers of the two calls above may also be DEVICE pointers (a snapshot assembled on the GPU, e.g. every rank
+ * of a multi-GPU job uploads 1/N of the cell-major fields and an all-gather over NVLink completes them; the reference has
+ * no counterpart, it re-uploads everything per call, src/GPU/CUDA/Kernel/MPASOVisualizerKernels.cu:2241-2272).  The
+ * copies run on the context's side stream: make that stream wait for the producer of the device buffers with
+ * mops_side_wait_event (a cudaEvent_t recorded on the producing stream) before mops_set_snapshot_async. */
+int mops_side_wait_event(mops_ctx* ctx, void* cuda_event);
 /* copy the prepared vertex-major arrays back in the caller's vertex order (parity tests):
  * ztop [nV][L], vel [nV][L][3], vertvel [nV][L+1] (level L is not kept by the engine and
  * reads back as 0 -- no kernel of the path uses it), attr [nV][L].  Any may be NULL.     */

@@ -28,7 +28,7 @@ STATUS_NAMES = {0: "alive", 1: "bad_cell", 2: "not_in_cell", 3: "bad_column", 4:
 # every symbol include/mops_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "mops_abi_version", "mops_create", "mops_destroy", "mops_last_error", "mops_host_alloc", "mops_host_free",
-    "mops_synchronize", "mops_set_stream", "mops_mark", "mops_elapsed_ms", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait",
+    "mops_synchronize", "mops_set_stream", "mops_mark", "mops_elapsed_ms", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait", "mops_side_wait_event",
     "mops_get_prepared", "mops_locate", "mops_streamline", "mops_pathline", "mops_finalize_lines",
     "mops_remap_fixed_depth", "mops_remap_fixed_layer", "mops_regrid_fixed_latitude", "mops_get_info",
 ]
@@ -106,6 +106,7 @@ def load_library():
     lib.mops_set_snapshot.argtypes = snap_args
     lib.mops_set_snapshot_async.argtypes = snap_args
     lib.mops_snapshot_wait.argtypes = [vp, i32]
+    lib.mops_side_wait_event.argtypes = [vp, vp]
     lib.mops_get_prepared.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.mops_locate.argtypes = [vp, i32, i64, vp, vp]
     lib.mops_streamline.argtypes = [vp, C.POINTER(TrajCfg), i32, C.POINTER(TrajIO), C.POINTER(TrajStats)]
@@ -210,6 +211,10 @@ class Engine:
         pa = (C.c_void_p * 1)()
         self._ck(fn(self.h, slot, n_levels, zonal, merid, thick, bottom, wtop, 0, pa, 0))
         self.levels[slot] = n_levels
+
+    def side_wait_event(self, cuda_event: int):
+        """the side stream (snapshot upload + preprocessing) waits for a cudaEvent_t recorded by the caller"""
+        self._ck(self.lib.mops_side_wait_event(self.h, C.c_void_p(cuda_event)))
 
     def snapshot_wait(self, slot):
         self._ck(self.lib.mops_snapshot_wait(self.h, slot))

@@ -337,11 +337,18 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
     if (wtop && (rc = ensure(ctx, ctx->st_wtop, nC * (L + 1) * 8))) return rc;
     if (n_attr > 0 && (rc = ensure(ctx, ctx->st_attr, nC * L * 8))) return rc;
 
-    CK(cudaMemcpyAsync(ctx->st_zonal.p, zonal, nC * L * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->st_merid.p, merid, nC * L * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->st_thick.p, thick, nC * L * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->st_bottom.p, bottom, nC * 8, cudaMemcpyHostToDevice, st));
-    if (wtop) CK(cudaMemcpyAsync(ctx->st_wtop.p, wtop, nC * (L + 1) * 8, cudaMemcpyHostToDevice, st));
+    // inputs are host pointers (the reference's vectors; pinned memory makes the copy asynchronous) or, for callers that
+    // assembled the snapshot on the device (e.g. an all-gather over NVLink of per-rank parts), device pointers
+    auto kind_of = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return cudaMemcpyHostToDevice; }
+        return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    };
+    CK(cudaMemcpyAsync(ctx->st_zonal.p, zonal, nC * L * 8, kind_of(zonal), st));
+    CK(cudaMemcpyAsync(ctx->st_merid.p, merid, nC * L * 8, kind_of(merid), st));
+    CK(cudaMemcpyAsync(ctx->st_thick.p, thick, nC * L * 8, kind_of(thick), st));
+    CK(cudaMemcpyAsync(ctx->st_bottom.p, bottom, nC * 8, kind_of(bottom), st));
+    if (wtop) CK(cudaMemcpyAsync(ctx->st_wtop.p, wtop, nC * (L + 1) * 8, kind_of(wtop), st));
 
     k_cell_ztop<<<blocks_for(ctx->nC, 128), 128, 0, st>>>((const double*)ctx->st_thick.p, (const double*)ctx->st_bottom.p,
                                                           (double*)ctx->st_ztopc.p, ctx->nC, L);
@@ -350,7 +357,7 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
         (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L);
     ctx->launches += 2;
     for (int a = 0; a < n_attr; ++a) {
-        CK(cudaMemcpyAsync(ctx->st_attr.p, attrs[a], nC * L * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->st_attr.p, attrs[a], nC * L * 8, kind_of(attrs[a]), st));
         k_vertex_scalar<<<blocks_for((long long)nV * L, 256), 256, 0, st>>>(ctx->vert, ctx->vcell_ext, (const double*)ctx->st_attr.p,
                                                                           s.attr[a], ctx->nV, L);
         ctx->launches++;
@@ -1238,6 +1245,14 @@ int mops_set_snapshot_async(mops_ctx* ctx, int32_t slot, int32_t n_levels, const
 {
     return set_snapshot_impl(ctx, slot, n_levels, zonal, meridional, layer_thickness, bottom_depth, vert_vel_top, n_attr, attrs,
                              n_attr_total, true);
+}
+
+int mops_side_wait_event(mops_ctx* ctx, void* cuda_event)
+{
+    if (!ctx || !cuda_event) return MOPS_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamWaitEvent(ctx->side, (cudaEvent_t)cuda_event, 0));
+    return MOPS_OK;
 }
 
 int mops_snapshot_wait(mops_ctx* ctx, int32_t slot)

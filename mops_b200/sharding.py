@@ -58,6 +58,36 @@ def gather_rows(local, counts: List[int], rank: int, world: int, dst: int = 0):
     return None
 
 
+def snapshot_part_bounds(total: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """The next snapshot does not have to cross every rank's PCIe link whole: its cell-major fields, concatenated
+    (zonal, meridional, layerThickness, bottomDepth = `total` doubles), are cut into `world` chunks of `chunk` doubles
+    (the last one zero-padded); rank r uploads [lo, hi) and an all-gather over NVLink completes the copy on every GPU.
+    Returns (chunk, lo, hi)."""
+    chunk = -(-total // max(world, 1))
+    lo = min(rank * chunk, total)
+    hi = min(lo + chunk, total)
+    return chunk, lo, hi
+
+
+def pack_snapshot_part(fields, rank: int, world: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """this rank's chunk of the concatenation of `fields` (arrays, flattened in C order), zero-padded to the chunk
+    length, without materialising the concatenation"""
+    flats = [np.asarray(f, dtype=np.float64).reshape(-1) for f in fields]
+    total = int(sum(f.shape[0] for f in flats))
+    chunk, lo, hi = snapshot_part_bounds(total, rank, world)
+    if out is None:
+        out = np.empty(chunk, dtype=np.float64)
+    assert out.shape == (chunk,)
+    out[hi - lo:] = 0.0
+    start = 0
+    for f in flats:
+        a, b = max(lo, start), min(hi, start + f.shape[0])
+        if a < b:
+            out[a - lo:b - lo] = f[a - start:b - start]
+        start += f.shape[0]
+    return out
+
+
 def scatter_back(global_n: int, parts, indices: List[np.ndarray]) -> np.ndarray:
     """reassemble gathered per-rank rows into caller (global seed) order"""
     import torch

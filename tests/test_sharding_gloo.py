@@ -57,3 +57,46 @@ def test_shard_gather_roundtrip(tmp_path):
     assert sec.min() == 0 and sec.max() == 7
     cnt = np.bincount(sec, minlength=8)
     assert abs(cnt - n / 8).max() < 0.1 * n / 8
+
+
+def _snapshot_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    from mops_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fields = _snapshot_fields()
+    total = sum(f.size for f in fields)
+    chunk, lo, hi = sharding.snapshot_part_bounds(total, rank, world)
+    part = torch.from_numpy(sharding.pack_snapshot_part(fields, rank, world))
+    assert part.shape[0] == chunk and hi - lo <= chunk
+    full = torch.empty(chunk * world, dtype=torch.float64)
+    dist.all_gather_into_tensor(full, part)  # NCCL over NVLink in bench.py --snapshot-allgather
+    if rank == 0:
+        np.save(out_path, full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _snapshot_fields():
+    rng = np.random.default_rng(5)
+    n_cells, L = 1003, 7  # sizes that do not divide evenly
+    return [rng.normal(size=(n_cells, L)), rng.normal(size=(n_cells, L)), rng.random((n_cells, L)), rng.random(n_cells)]
+
+
+def test_partitioned_snapshot_allgather(tmp_path):
+    """every rank packs 1/world of the concatenated cell-major fields; the all-gather reproduces the whole snapshot,
+    field boundaries and the zero padding of the last chunk included"""
+    from mops_b200 import sharding
+    world = 3
+    out = str(tmp_path / "snap.npy")
+    mp.spawn(_snapshot_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    fields = _snapshot_fields()
+    flat = np.concatenate([f.reshape(-1) for f in fields])
+    full = np.load(out)
+    assert np.array_equal(full[:flat.shape[0]], flat)
+    assert not full[flat.shape[0]:].any()
+    # bounds are a partition of [0, total)
+    edges = [sharding.snapshot_part_bounds(flat.shape[0], r, world) for r in range(world)]
+    assert edges[0][1] == 0 and edges[-1][2] == flat.shape[0]
+    assert all(edges[r][2] == edges[r + 1][1] for r in range(world - 1))
