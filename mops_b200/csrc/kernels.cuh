@@ -383,6 +383,9 @@ __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : (
 #ifndef MOPS_ADV_MINB
 #define MOPS_ADV_MINB 3
 #endif
+#ifndef MOPS_ROLL_RELOC
+#define MOPS_ROLL_RELOC 0 // 1 = rolled cell relocation (smaller hot code); not yet measured on B200
+#endif
 // SEG = true: the launch covers steps [P.step_begin, P.step_end) only (see AdvectParams::state); SEG = false is the
 // single-launch kernel (every SEG-only branch folds away at compile time).
 template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR, bool SEG = false>
@@ -434,6 +437,49 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                 if (step > 0) {
                     // relocation: argmin over {cellsOnCell[c][0..nv-1], c} of |centre - x|, strict <,
                     // that order, one ring (VK:903-921; GetCellNeighborsIdx TK:74-101)
+#if MOPS_ROLL_RELOC
+                    // rolled form (one candidate at a time, three short loops): same candidates, same order, same
+                    // compares as the unrolled form below, in ~1/5 of its instruction footprint -- relocation runs once
+                    // per step, the evaluation four times, and the kernel's hot code sits at the L1.5 I-cache size
+                    const CellRec<M>* r = recs + cell;
+                    int best = cell;
+                    double m1 = 1.7976931348623157e308;
+#pragma unroll 1
+                    for (int k = 0; k <= M; ++k) {
+                        const int c = (k < M) ? r->nbr[k] : cell;
+                        if (c >= 0) {
+                            const double4 cc = ldg_d4(P.c4 + c);
+                            const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
+                            const double l = dx * dx + dy * dy + dz * dz;
+                            if (l < m1) { m1 = l; best = c; }
+                        }
+                    }
+                    const double lim = m1 + m1 * 0x1p-48;
+                    int close = 0;
+#pragma unroll 1
+                    for (int k = 0; k <= M; ++k) {
+                        const int c = (k < M) ? r->nbr[k] : cell;
+                        if (c >= 0) {
+                            const double4 cc = ldg_d4(P.c4 + c);
+                            const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
+                            close += (dx * dx + dy * dy + dz * dz <= lim) ? 1 : 0;
+                        }
+                    }
+                    if (close > 1 || !(m1 < 1.0e300)) { // near-tie: compare the roots as the reference does
+                        double min_len = 1.7976931348623157e308;
+                        best = cell;
+#pragma unroll 1
+                        for (int k = 0; k <= M; ++k) {
+                            const int c = (k < M) ? r->nbr[k] : cell;
+                            if (c >= 0) {
+                                const double4 cc = ldg_d4(P.c4 + c);
+                                const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
+                                const double l = slow_sqrt(dx * dx + dy * dy + dz * dz);
+                                if (l < min_len) { min_len = l; best = c; }
+                            }
+                        }
+                    }
+#else
                     const CellRec<M>* r = recs + cell;
                     const int nv = r->nv;
                     double min_len = 1.7976931348623157e308;
@@ -475,6 +521,7 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                         for (int k = 0; k <= M; ++k)
                             if (cand[k] >= 0 && len[k] < min_len) { min_len = len[k]; best = cand[k]; }
                     }
+#endif
                     if (best != cell) { cell = best; }
                     // walk mode: not limited to one ring (identical whenever the step is shorter than a cell)
                     if (EXTRA && P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
