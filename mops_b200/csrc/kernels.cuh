@@ -370,6 +370,27 @@ __device__ __forceinline__ void st3(double* p, long long i, double x, double y, 
 
 __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : ((1.0 < v) ? 1.0 : v); }
 
+#ifndef MOPS_COLD_GENERIC
+#define MOPS_COLD_GENERIC 0 // 1 = the generic (nv != record width) evaluation of 6-wide meshes is a call; not yet measured on B200
+#endif
+struct EvalPacked {
+    EvalOut o;
+    int st, hint_f, hint_b;
+};
+template <int M, bool PATH>
+__device__ __noinline__ EvalPacked eval_generic_cold(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv, bool mf, bool mb,
+                                                     int L, int attr_count, double px, double py, double pz, double depth, double alpha,
+                                                     int hint_f, int hint_b)
+{
+    EvalPacked r;
+    r.hint_f = hint_f; r.hint_b = hint_b;
+    r.o.hx = 0.0; r.o.hy = 0.0; r.o.hz = 0.0; r.o.vv = 0.0; r.o.a0 = 0.0; r.o.a1 = 0.0;
+    const d3 p = mk3(px, py, pz);
+    r.st = PATH ? eval_path<M>(rec, sv, mf, mb, L, attr_count, p, depth, alpha, r.hint_f, r.hint_b, r.o)
+                : eval_stream<M>(rec, sv[0], mf, L, p, depth, r.hint_f, r.o);
+    return r;
+}
+
 // EXTRA = false is the production instantiation; EXTRA = true additionally honours P.walk
 // (MOPS_SEM_WALK) and P.diag_edge (near-edge counting) -- kept out of the hot variant because even
 // never-taken branches cost registers and ~4 % of the kernel time here.
@@ -566,12 +587,20 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                         if (a < edge_min) edge_min = a;
                     }
                     // hexagon fast path: with nv == M every per-slot select of the evaluation folds away
-                    if (M == 6 && rec_s->nv == M)
+                    if (M == 6 && rec_s->nv == M) {
                         st = PATH ? eval_path<M, true>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
                                   : eval_stream<M, true>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
-                    else
+                    } else {
+#if MOPS_COLD_GENERIC
+                        if (M == 6) { // the 12 pentagons (and coast cells) of a hexagonal mesh: out of line, so the hot code stays contiguous
+                            const EvalPacked r = eval_generic_cold<M, PATH>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p.x, p.y, p.z,
+                                                                            cur_depth, a_s, hint_f, hint_b);
+                            st = r.st; hint_f = r.hint_f; hint_b = r.hint_b; o = r.o;
+                        } else
+#endif
                         st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
                                   : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
+                    }
                     if (st != ST_ALIVE) break;
                     if (s == 0) {
                         hvel = mk3(o.hx, o.hy, o.hz);
