@@ -472,6 +472,24 @@ __device__ __forceinline__ double gather_scalar(const double* __restrict__ a, co
     return r;
 }
 
+#ifndef MOPS_SQ_FILTER
+#define MOPS_SQ_FILTER 0 // 1 = the streamline's zero-velocity tests decide on the squared norm when it is far from 1e-24; not yet measured
+#endif
+// MOPS_LENGTH(v) < 1e-12 (VK:845-852).  With the filter: sqrt is monotone and correctly rounded, so a squared norm
+// >= 2e-24 has a root >= 1.41e-12 and one <= 0.5e-24 a root <= 0.71e-12 -- only the band in between (and NaN, for which
+// both compares are false) takes the root, and the decision is the reference's in every case.
+__device__ __forceinline__ bool tiny_len(double x, double y, double z)
+{
+#if MOPS_SQ_FILTER
+    const double s = x * x + y * y + z * z;
+    if (s >= 2.0e-24) return false;
+    if (s <= 0.5e-24) return true;
+    return sqrt(s) < 1e-12;
+#else
+    return len3(x, y, z) < 1e-12;
+#endif
+}
+
 struct EvalOut {
     double hx, hy, hz; // horizontal velocity (XYZ)
     double vv;         // vertical velocity
@@ -507,12 +525,12 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
 
     double dx, dy, dz, dw, ux, uy, uz, uw;
     gather_velw_pair<M, FULL>(s.velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
-    if (len3(dx, dy, dz) < 1e-12 || len3(ux, uy, uz) < 1e-12) return ST_ZERO_VELOCITY; // VK:845-847
+    if (tiny_len(dx, dy, dz) || tiny_len(ux, uy, uz)) return ST_ZERO_VELOCITY; // VK:845-847
     const double omt = 1.0 - t;
     o.hx = t * ux + omt * dx; // VK:849
     o.hy = t * uy + omt * dy;
     o.hz = t * uz + omt * dz;
-    if (len3(o.hx, o.hy, o.hz) < 1e-12) return ST_ZERO_VELOCITY;
+    if (tiny_len(o.hx, o.hy, o.hz)) return ST_ZERO_VELOCITY;
     o.vv = t * uw + omt * dw; // VK:870 (levels `layer`, `layer-1` of vertVelocityTop)
     o.a0 = 0.0; o.a1 = 0.0;
     return ST_ALIVE;

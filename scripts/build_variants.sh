@@ -4,6 +4,7 @@
 #   roll_reloc    -DMOPS_ROLL_RELOC=1    rolled once-per-step cell relocation (smaller hot code)
 #   cold_generic  -DMOPS_COLD_GENERIC=1  generic (non-hexagon) evaluation of 6-wide meshes out of line
 #   roll_cold     both
+#   sq_filter     -DMOPS_SQ_FILTER=1     streamline zero-velocity tests on the squared norm (time it with scripts/bench_secondary.py: C3)
 # Parity for a variant: MOPS_B200_LIB=$PWD/build_variants/<name>.so python -m pytest tests -m gpu -q
 set -euo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
@@ -13,4 +14,5 @@ b base &
 b roll_reloc -DMOPS_ROLL_RELOC=1 &
 b cold_generic -DMOPS_COLD_GENERIC=1 &
 b roll_cold -DMOPS_ROLL_RELOC=1 -DMOPS_COLD_GENERIC=1 &
+b sq_filter -DMOPS_SQ_FILTER=1 &
 wait
