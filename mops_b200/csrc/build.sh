@@ -9,5 +9,5 @@ OUT="${MOPS_OUT:-$HERE/../libmops_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
     -Xcompiler -fPIC,-O2,-fno-fast-math -shared ${MOPS_PTXAS_V:+-Xptxas -v} ${MOPS_DEFS:-} \
-    -o "$OUT" "$HERE/engine.cu" -lcudart
+    -o "$OUT" "$HERE/engine.cu" -lcudart -lpthread
 echo "built $OUT"

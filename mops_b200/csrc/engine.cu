@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1409,7 +1410,10 @@ int mops_finalize_lines(int64_t n, int32_t each, const double* seeds, const doub
     if (n < 0 || each <= 0 || (n > 0 && (!seeds || !raw_pos || !raw_vel || !points || !velocity))) return MOPS_E_INVALID;
     const int64_t per = (int64_t)each + 1;
     auto finite = [](const double* p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); };
-    for (int64_t i = 0; i < n; ++i) {
+    // lines are independent: large calls are split over the host cores (1 M lines x 169 points is ~2 s on one core, which
+    // would dwarf the kernels that produced them)
+    auto run = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
         double* P = points + i * per * 3;
         double* V = velocity + i * per * 3;
         double* T = temperature ? temperature + i * per : nullptr;
@@ -1447,6 +1451,22 @@ int mops_finalize_lines(int64_t n, int32_t each, const double* seeds, const doub
             }
         }
         if (last) std::memcpy(last + 3 * i, P + 3 * (per - 1), 24);
+    }
+    };
+    const int64_t min_chunk = std::max<int64_t>(1, (1 << 20) / per); // ~1 M points per task at least
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("MOPS_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+    nt = (unsigned)std::min<int64_t>(std::max(1u, std::min(nt, 64u)), (n + min_chunk - 1) / min_chunk);
+    if (nt <= 1) {
+        run(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        const int64_t chunk = (n + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            const int64_t lo = (int64_t)t * chunk, hi = std::min(n, lo + chunk);
+            if (lo < hi) pool.emplace_back(run, lo, hi);
+        }
+        for (auto& th : pool) th.join();
     }
     return MOPS_OK;
 }

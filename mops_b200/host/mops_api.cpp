@@ -4,6 +4,7 @@
 // into libmops_b200.so (CUDA kernels) -- there is no host implementation of the path here.
 #include "api/MOPS.h"
 #include "mops_b200.h"
+#include "lines.hpp"
 
 #include <execinfo.h>
 #include <signal.h>
@@ -15,7 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <memory>
 #include <mutex>
+#include <thread>
 
 namespace MOPS {
 
@@ -416,7 +419,9 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, in
         return lines;
     }
     std::vector<CartesianCoord> pos = seeds; // stable_points
-    std::vector<double> raw_pos(n * each * 3), raw_vel(n * each * 3);
+    // the engine writes every slot of both buffers (zeros for the slots a stopped particle never reaches), so they are
+    // not value-initialised here: at 1 M seeds x 168 records that alone would be 8 GB of serial zero-fill
+    std::unique_ptr<double[]> raw_pos(new double[n * each * 3]), raw_vel(new double[n * each * 3]);
     mops_traj_cfg cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.method = (config->methodType == CalcMethodType::kEuler) ? MOPS_METHOD_EULER : MOPS_METHOD_RK4;
@@ -432,8 +437,8 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, in
     io.xyz = reinterpret_cast<double*>(pos.data());
     io.depth = depths.data();
     io.cell0 = nullptr; // located on the device (replaces MPASOField::calcInWhichCells)
-    io.out_pos = raw_pos.data();
-    io.out_vel = raw_vel.data();
+    io.out_pos = raw_pos.get();
+    io.out_vel = raw_vel.get();
     mops_traj_stats st;
     const int rc = path ? mops_pathline(ctx, &cfg, slot_f, slot_b, &io, &st) : mops_streamline(ctx, &cfg, slot_f, &io, &st);
     if (rc != MOPS_OK) {
@@ -444,25 +449,8 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, in
     book().add(std::string("MemoryCopy::") + what, 3, st.total_ms - st.kernel_ms - st.locate_ms);
 
     // line assembly + NaN trimming (TrajectoryCommon.h:43-190) on the flat buffers
-    const size_t per = each + 1;
-    std::vector<double> pts(n * per * 3), vel(n * per * 3), temp(n * per), sal(n * per), last(n * 3);
-    mops_finalize_lines(static_cast<int64_t>(n), static_cast<int32_t>(each), reinterpret_cast<const double*>(seeds.data()), raw_pos.data(),
-                        raw_vel.data(), path ? 1 : 0, pts.data(), vel.data(), temp.data(), sal.data(), last.data());
-    lines.resize(n);
-    for (size_t i = 0; i < n; ++i) {
-        TrajectoryLine& ln = lines[i];
-        ln.lineID = static_cast<int>(i);
-        ln.points.resize(per);
-        ln.velocity.resize(per);
-        std::memcpy(ln.points.data(), pts.data() + i * per * 3, per * 24);
-        std::memcpy(ln.velocity.data(), vel.data() + i * per * 3, per * 24);
-        ln.temperature.assign(temp.begin() + i * per, temp.begin() + (i + 1) * per);
-        ln.salinity.assign(sal.begin() + i * per, sal.begin() + (i + 1) * per);
-        ln.lastPoint = CartesianCoord(last[3 * i], last[3 * i + 1], last[3 * i + 2]);
-        ln.duration = static_cast<double>(config->simulationDuration);
-        ln.timestamp = static_cast<double>(config->deltaT);
-        ln.depth = depths0[i];
-    }
+    lines = detail::assemble_lines(n, each, seeds.data(), raw_pos.get(), raw_vel.get(), path, static_cast<double>(config->simulationDuration),
+                                   static_cast<double>(config->deltaT), depths0.data());
     return lines;
 }
 } // namespace

@@ -92,3 +92,26 @@ def test_nan_trimming_cases_of_reference_test():
         b = P.finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=bool(mode))
         for x, k in zip(a, ("points", "velocity", "temperature", "salinity", "last")):
             assert np.array_equal(x, b[k], equal_nan=True), k
+
+
+def test_finalize_lines_threaded_equals_serial(monkeypatch):
+    """large calls are split over the host cores (MOPS_HOST_THREADS overrides the count): same bytes either way, and
+    equal to the oracle restatement"""
+    lib, capi = _lib()
+    rng = np.random.default_rng(3)
+    n, each = 30000, 40  # 1.2 M points: above the threshold where threads are used
+    seeds = rng.normal(size=(n, 3)); raw_pos = rng.normal(size=(n, each, 3)); raw_vel = rng.normal(size=(n, each, 3))
+    raw_pos[::11, 17:, :] = np.nan
+    raw_pos[5, 0, 0] = np.inf
+    seeds[13, 2] = np.nan
+    out = {}
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("MOPS_HOST_THREADS", threads)
+        out[threads] = _finalize(capi, seeds, raw_pos, raw_vel, 1)
+    for threads in ("3", "8"):
+        for a, b in zip(out["1"], out[threads]):
+            assert np.array_equal(a, b, equal_nan=True)
+    from oracle import port_oracle as P
+    ref = P.finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=True)
+    for x, k in zip(out["8"], ("points", "velocity", "temperature", "salinity", "last")):
+        assert np.array_equal(x, ref[k], equal_nan=True), k

@@ -7,7 +7,7 @@ ROOT="$HERE/.."
 CXX="${CXX:-g++}"
 CUDA_LIB="${CUDA_HOME:-/usr/local/cuda}/lib64"
 $CXX -std=c++17 -O2 -fPIC -shared -I"$ROOT/include" -o "$ROOT/mops_b200/libmops_api.so" "$ROOT/mops_b200/host/mops_api.cpp" "$ROOT/mops_b200/host/mops_reader.cpp" "$ROOT/mops_b200/host/mpas_io.cpp" -I"$ROOT/mops_b200/host" \
-    -L"$ROOT/mops_b200" -lmops_b200 -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$CUDA_LIB"
+    -L"$ROOT/mops_b200" -lmops_b200 -pthread -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$CUDA_LIB"
 mkdir -p "$HERE/bin"
 for t in streamLine pathLine reMapping; do
     $CXX -std=c++17 -O2 -I"$ROOT/include" -I"$HERE" -o "$HERE/bin/$t" "$HERE/$t.cpp" \
