@@ -6,26 +6,31 @@ Workload (config C5 of BASELINE.json): pathline, 64 M seeds (stron
 solid-body-rotation snapshots, RK4, dt = 120 s, depth 800 m.  One bench "step" = one
 MOPS_RunPathLine-equivalent call (mops_pathline through the C ABI) over one snapshot interval
 of `--interval-steps` RK4 steps (default 120 of the 720 a 1-day interval has, so that the
-default run ends within minutes; throughput is per particle-step), chained the way the
-reference's tutorial chains intervals (end points -> next seeds, re-located), while the NEXT
-snapshot is uploaded + preprocessed on the side stream from pinned host memory
-(double-buffered H2D).  Executed particle-steps (alive at step start) are counted by the
-kernel itself.
+default run ends within minutes; throughput is per particle-step), while the NEXT snapshot is
+uploaded + preprocessed on the side stream from pinned host memory (double-buffered H2D).
+
+Every step integrates the SAME fresh seed set (particles are reset at the start of the step, a
+device-to-device copy inside the timed region): under the reference's semantics a particle stops
+for good at its first failed RK4 stage, so a chain that fed end points back in would execute a
+shrinking fraction of its steps and `value` would depend on --steps.  Executed particle-steps
+(alive at step start) are counted by the kernel itself; `config.executed_fraction` reports them.
 
   value        : device-resident arm (particles/outputs stay in HBM), K timed steps, max over ranks
-  e2e          : same call with HOST buffers (pinned): seeds/depths H2D and recorded
-                 trajectories D2H inside the timed region
-  roofline     : k_advect launches only (CUDA events on the launching stream, from the C ABI's
-                 stats), algorithmic bytes per step of SURVEY.md 8(d)
+  e2e          : the HOST-memory form of the same call (mops_pathline_submit / mops_traj_wait, pinned
+                 buffers): seeds/depths H2D and end points + recorded trajectories D2H inside the timed
+                 region, two staging sets so that the copies of one step overlap the kernels of the next
+  roofline     : k_advect launches only (CUDA events on the launching stream, from the C ABI's stats).
+                 The kernel is bound by the fp64 pipe, not by HBM (sorted particles share cells, L1 hit
+                 98 %): `frac` is the fp64-pipe fraction, the contract's HBM figures sit beside it
   cpu_baseline : the reference's own TBB/CPU implementation (oracle/_ref, compiled unmodified)
-                 on the host cores, bounded sample (N = 1, rank 0 only)
+                 on the host cores, bounded sample (N = 1, rank 0 only); `parity_sample` compares the
+                 GPU on exactly that sample with the reference
 
 `--impl reference` times only the reference CPU arm and prints the same JSON shape.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import math
 import os
@@ -43,11 +48,16 @@ DT = 120
 DEPTH = 800.0
 METRIC = "particle RK4 steps/sec (pathline, executed particle-steps)"
 UNIT = "particle-steps/s"
+R_SEED = 6371010.0
 
 
-def algorithmic_bytes_per_step(L: int, pathline: bool) -> int:
-    """int32 indices, fp64 payload, nv = 6, minimal K = 2*ceil(log2(L-1)) + 2."""
-    K = 2 * math.ceil(math.log2(L - 1)) + 2
+def layer_levels_contract(L: int) -> int:
+    """SURVEY.md 8(d) contract figure: minimal K = 2*ceil(log2(L-1)) + 2 zTop levels per vertex"""
+    return 2 * math.ceil(math.log2(L - 1)) + 2
+
+
+def algorithmic_bytes_per_step(L: int, pathline: bool, K: int) -> int:
+    """int32 indices, fp64 payload, nv = 6, K zTop levels read per vertex and evaluation"""
     per_eval = (172 + 2 * (48 * K + 384)) if pathline else (556 + 48 * K)
     return 4 * per_eval + 196 + 64
 
@@ -56,10 +66,21 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
+
+
+def load_profile(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
 
 
 class ClockSampler:
@@ -125,33 +146,44 @@ def make_snapshot_host(mesh, L, speed, tilt, pinned_alloc):
     return bufs
 
 
-def run_cpu_reference(level, L, n_particles, interval_steps, threads=None, target_seconds=12.0, repeats=1, log=None):
-    """Times the reference's TBB/CPU PathLine on the host cores (oracle/_ref).  Returns dict or None."""
+def cpu_sample_inputs(level, L):
+    """mesh, the two snapshots and the seed pool of the CPU-baseline / parity sample (same generators as the GPU workload)"""
+    from mops_b200 import synthetic as S
+    mesh = S.icosahedral_mesh(level)
+    s0 = S.solid_body_snapshot(mesh, L, 0.02, tilt=0.3)
+    s1 = S.solid_body_snapshot(mesh, L, 0.025, tilt=0.31)
+    return mesh, s0, s1
+
+
+def run_cpu_reference(level, L, n_particles, interval_steps, threads=None, target_seconds=12.0, repeats=1, keep_lines=False):
+    """Times the reference's TBB/CPU PathLine on the host cores (oracle/_ref).  Returns dict."""
     from mops_b200 import synthetic as S
     try:
         from oracle import ref_oracle as R
         have_ref = R.available()
     except Exception:
         have_ref = False
-    mesh = S.icosahedral_mesh(level)
-    s0 = S.solid_body_snapshot(mesh, L, 0.02, tilt=0.3)
-    s1 = S.solid_body_snapshot(mesh, L, 0.025, tilt=0.31)
+    mesh, s0, s1 = cpu_sample_inputs(level, L)
     seeds_all = S.uniform_sphere_seeds(n_particles, 20261018 + 5)
     duration = DT * interval_steps
+    record_t = min(3600, duration)
+    lines = None
     if have_ref:
-        cores = R.max_threads() if threads is None else threads
+        # all host cores, set explicitly: under torchrun OMP_NUM_THREADS=1 is exported and omp_get_max_threads() obeys it
+        cores = int(threads or os.cpu_count() or 1)
         R.set_threads(cores)
         o = R.RefOracle(mesh, [s0, s1])
         o.activate(0, 1)
-        # probe to size the sample for ~target_seconds
         probe_n = min(n_particles, 20000)
-        r = o.pathline(seeds_all[:probe_n], DT, duration, min(3600, duration), depth=DEPTH)
+        r = o.pathline(seeds_all[:probe_n], DT, duration, record_t, depth=DEPTH)
         rate = probe_n * interval_steps / max(r["seconds"], 1e-6)
         n = int(min(n_particles, max(probe_n, rate * target_seconds / interval_steps)))
         times = []
         for _ in range(repeats):
-            r = o.pathline(seeds_all[:n], DT, duration, min(3600, duration), depth=DEPTH)
+            r = o.pathline(seeds_all[:n], DT, duration, record_t, depth=DEPTH)
             times.append(r["seconds"])
+        if keep_lines:
+            lines = {"points": r["points"], "velocity": r["velocity"]}
         o.close()
         kind = "reference"
     else:
@@ -163,21 +195,84 @@ def run_cpu_reference(level, L, n_particles, interval_steps, threads=None, targe
         times = []
         for _ in range(repeats):
             t0 = time.perf_counter()
-            P.pathline(mesh, p0, p1, seeds_all[:n], cell0, DT, duration, duration, depth=DEPTH, log_cells=False)
+            P.pathline(mesh, p0, p1, seeds_all[:n], cell0, DT, duration, record_t, depth=DEPTH, log_cells=False)
             times.append(time.perf_counter() - t0)
         kind = "port"
-    # executed particle-steps of the sample: counted with the scalar port (bit-identical decisions)
+    # executed particle-steps + per-step cell ids of a subsample: the scalar port (bit-identical to the reference, logs ids)
     from oracle import port_oracle as P
     p0, p1 = P.prepare(mesh, s0), P.prepare(mesh, s1)
     sub = min(n, 20000)
     cell0 = P.locate(mesh, seeds_all[:sub])
-    pr = P.pathline(mesh, p0, p1, seeds_all[:sub], cell0, DT, duration, duration, depth=DEPTH, log_cells=False)
+    pr = P.pathline(mesh, p0, p1, seeds_all[:sub], cell0, DT, duration, record_t, depth=DEPTH, log_cells=True)
     alive_frac = float(pr["steps_alive"].sum()) / float(sub * interval_steps)
     steps = n * interval_steps * alive_frac
-    return {"kind": kind, "cores": int(cores), "times": times, "particle_steps": steps, "n": n,
+    return {"kind": kind, "cores": int(cores), "times": times, "particle_steps": steps, "n": n, "sub": sub,
+            "mesh": mesh, "snaps": (s0, s1), "seeds": seeds_all[:n], "lines": lines, "port": pr, "record_t": record_t,
+            "duration": duration,
             "sample": f"pathline, {n} seeds x {interval_steps} RK4 steps, {mesh.n_cells}-cell x {L}-layer mesh "
                       f"(same generator, level {level}), dt={DT}s, depth {DEPTH:.0f} m; includes the reference's host KD-tree "
                       f"lookup and line assembly (MOPS_RunPathLine wall time); executed fraction {alive_frac:.4f}"}
+
+
+def parity_on_sample(res, device):
+    """GPU vs the reference on exactly the sample the CPU arm integrated (outside every timed region): recorded
+    positions / velocities of all its seeds against the compiled reference's lines, per-step cell ids of a subsample
+    against the restatement's log, near-edge count (1e-12 rad band) from the diagnostic instantiation."""
+    from mops_b200 import capi
+    mesh, (s0, s1), seeds = res["mesh"], res["snaps"], res["seeds"]
+    eng = capi.Engine(device)
+    try:
+        eng.set_mesh(mesh)
+        eng.set_snapshot(0, s0)
+        eng.set_snapshot(1, s1)
+        g = eng.pathline(0, 1, seeds, DT, res["duration"], res["record_t"], depth=DEPTH, want_attr=False)
+        sub = res["sub"]
+        gs = eng.pathline(0, 1, seeds[:sub], DT, res["duration"], res["record_t"], depth=DEPTH, want_attr=False, log_cells=True,
+                          near_edge=True)
+        out = {"n": int(seeds.shape[0]), "cell_id_subsample": int(sub),
+               "cell_mismatch": int(np.count_nonzero(gs["cell_log"] != res["port"]["cell_log"])),
+               "near_edge_particles_subsample": int(gs["stats"].near_edge_particles)}
+        if res["lines"] is not None:
+            lines = eng.finalize_lines(seeds, g["raw_pos"], g["raw_vel"], pathline_mode=True)
+            dx = np.linalg.norm(lines["points"] - res["lines"]["points"], axis=2)
+            rv = res["lines"]["velocity"]
+            dv = np.linalg.norm(lines["velocity"] - rv, axis=2) / np.maximum(np.linalg.norm(rv, axis=2), 1e-300)
+            dv = np.where(np.linalg.norm(rv, axis=2) > 0, dv, 0.0)
+            out.update({"against": "oracle/_ref (compiled reference) lines + oracle port cell log",
+                        "max_dx_m": float(dx.max()), "max_rel_dv": float(dv.max()),
+                        "bit_identical": bool(np.array_equal(lines["points"], res["lines"]["points"])
+                                              and np.array_equal(lines["velocity"], rv))})
+        else:
+            dx = np.linalg.norm(gs["raw_pos"] - res["port"]["raw_pos"], axis=2)
+            out.update({"against": "oracle port (reference not compiled on this box)", "max_dx_m": float(dx.max()),
+                        "bit_identical": bool(np.array_equal(gs["raw_pos"], res["port"]["raw_pos"]))})
+        return out, eng
+    except Exception:
+        eng.close()
+        raise
+
+
+def remap_secondary(eng, mesh, torch):
+    """BASELINE metric's second half: remap pixels/s on C2 (level-7 mesh x 60 layers, depth 800 m), device-resident
+    kernel time and end to end with the image copied back to host memory"""
+    from mops_b200 import capi, synthetic as S
+    s = S.solid_body_snapshot(mesh, 60, 0.5, tilt=0.3)
+    eng.set_snapshot(2, s)
+    out = {}
+    for (w, h) in ((360, 180), (3600, 1800)):
+        img = torch.empty((h, w, 4), dtype=torch.float64, device="cuda")
+        cfg = capi.RemapCfg(w, h, -90.0, 90.0, -180.0, 180.0, 800.0, capi.MEM_DEVICE)
+        for _ in range(3):
+            eng.remap_device(2, cfg, img)
+        kms = float(np.median([eng.remap_device(2, cfg, img).kernel_ms for _ in range(10)]))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r = eng.remap(2, w, h, depth=800.0, want_attr=False, want_cells=False)
+        e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+        out[f"{w}x{h}"] = {"pixels_per_s": w * h / (kms / 1e3), "kernel_ms": kms, "pixels_per_s_e2e_host_image": w * h / (e2e_ms / 1e3),
+                           "nan_pixels": int(r["stats"].nan_pixels)}
+    out["config"] = "C2: 163,842 cells x 60 layers, depth 800 m, lat/lon full range; kernel = locate + interpolate per pixel"
+    return out
 
 
 def main():
@@ -188,16 +283,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--level", type=int, default=9, help="icosahedral bisection level (9 = 2,621,442 cells)")
     ap.add_argument("--layers", type=int, default=80)
-    ap.add_argument("--sweep-host-chunk", type=str, default="", help="experiment: comma list of HOST-mode chunk sizes to time")
     ap.add_argument("--particles", type=int, default=64_000_000, help="TOTAL seeds over all GPUs (strong scaling)")
     ap.add_argument("--interval-steps", type=int, default=120, help="RK4 steps per snapshot interval (720 = 1 day)")
     ap.add_argument("--cpu-level", type=int, default=7)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
-    ap.add_argument("--snapshot-allgather", action="store_true",
-                    help="N > 1: every rank uploads 1/N of the next snapshot over PCIe and an NCCL all-gather over NVLink "
-                         "completes it on every GPU (default: every rank uploads the whole snapshot itself)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the near-edge pass, the parity sample and the remap figures")
+    ap.add_argument("--chain", action="store_true", help="feed end points back in instead of resetting the particles every step")
+    ap.add_argument("--snapshot-upload", default="auto", choices=["auto", "replicated", "allgather"],
+                    help="N > 1: 'allgather' = every rank uploads 1/N of the next snapshot over PCIe and an NCCL all-gather over "
+                         "NVLink completes it on every GPU; 'replicated' = every rank uploads the whole snapshot; auto = allgather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,7 +303,8 @@ def main():
     L = args.layers
     workload = (f"C5 pathline: {args.particles} seeds total, icosahedral level {args.level} "
                 f"({10 * 4 ** args.level + 2} cells) x {L} layers, RK4 dt={DT}s, depth {DEPTH:.0f} m, "
-                f"{args.interval_steps} RK4 steps per snapshot interval, next snapshot double-buffered H2D")
+                f"{args.interval_steps} RK4 steps per snapshot interval (C5 as written: 720), next snapshot double-buffered H2D, "
+                f"{'chained end points' if args.chain else 'fresh seeds every step'}")
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -230,7 +327,7 @@ def main():
     # ------------------------------------------------------------------ our arm
     import torch
     import torch.distributed as dist
-    from mops_b200 import capi, synthetic as S
+    from mops_b200 import capi, sharding, synthetic as S
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
@@ -245,36 +342,36 @@ def main():
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     eng.set_mesh(mesh)
 
-    def pinned(shape):
-        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
 
     # distinct host snapshots (pinned); snapshot s of the chain re-uses ring[s % len(ring)].  Two when host
     # memory allows (all ranks of the box pin theirs at once), else one.
+    use_ag = world > 1 and args.snapshot_upload in ("auto", "allgather")
     snap_host_bytes = 3 * mesh.n_cells * L * 8
     ring_n = 2
     try:
         avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
-        if world * (2 * snap_host_bytes + 8e9) > 0.6 * avail:
+        per_rank = (2 * snap_host_bytes / (world if use_ag else 1)) + 40e9 / world
+        if world * per_rank > 0.6 * avail:
             ring_n = 1
     except Exception:
         pass
     ring = [make_snapshot_host(mesh, L, 0.02 * (1 + 0.5 * math.sin(2 * math.pi * s / 30)), 0.3 + 0.01 * s, pinned)
             for s in range(ring_n)]
 
-    # N > 1, opt-in: partitioned upload + all-gather (SURVEY 8e "broadcast of each new snapshot").  Each rank keeps only its
-    # 1/N chunk of the concatenated cell-major fields in pinned memory; the chunk goes over this rank's PCIe link on a
-    # private torch stream, an all-gather on a private NCCL communicator assembles the snapshot in HBM (double-buffered:
-    # the engine's side stream copies out of it asynchronously), and the engine takes DEVICE pointers.
-    use_ag = bool(args.snapshot_allgather) and world > 1
+    # N > 1: partitioned upload + all-gather (SURVEY 8e "broadcast of each new snapshot").  Each rank keeps only its 1/N chunk
+    # of the concatenated cell-major fields in pinned memory; the chunk goes over this rank's PCIe link on a private torch
+    # stream, an all-gather on a private NCCL communicator assembles the snapshot in HBM (double-buffered: the engine's side
+    # stream copies out of it asynchronously), and the engine takes DEVICE pointers.
+    nfield = mesh.n_cells * L
     if use_ag:
-        from mops_b200 import sharding as _sh
-        nfield = mesh.n_cells * L
         ag_total = 3 * nfield + mesh.n_cells
-        ag_chunk, _, _ = _sh.snapshot_part_bounds(ag_total, rank, world)
+        ag_chunk, _, _ = sharding.snapshot_part_bounds(ag_total, rank, world)
         ring_parts = []
         for h in ring:
             part_h = pinned((ag_chunk,))
-            _sh.pack_snapshot_part([h["zonal"], h["merid"], h["thick"], h["bottom"]], rank, world, out=part_h)
+            sharding.pack_snapshot_part([h["zonal"], h["merid"], h["thick"], h["bottom"]], rank, world, out=part_h)
             ring_parts.append(torch.from_numpy(part_h))
         ring = None  # the whole-snapshot host copies are not needed in this mode
         ag_group = dist.new_group(backend="nccl")
@@ -282,10 +379,15 @@ def main():
         ag_full = [torch.empty(ag_chunk * world, dtype=torch.float64, device=dev) for _ in range(2)]
         ag_part = torch.empty(ag_chunk, dtype=torch.float64, device=dev)
         ag_event = [torch.cuda.Event() for _ in range(2)]
+        ag_slot = [None, None]  # engine slot that consumed ag_full[k] last
 
     def upload(slot, s, async_):
         if use_ag:
             k = s % 2
+            if ag_slot[k] is not None:
+                # the engine's side stream may still be copying out of ag_full[k] (the previous upload that used it):
+                # its `ready` event covers those copies, so wait for it before the all-gather overwrites the buffer
+                eng.snapshot_wait(ag_slot[k])
             with torch.cuda.stream(ag_stream):
                 ag_part.copy_(ring_parts[s % ring_n], non_blocking=True)
                 dist.all_gather_into_tensor(ag_full[k], ag_part, group=ag_group)
@@ -293,6 +395,7 @@ def main():
             eng.side_wait_event(ag_event[k].cuda_event)
             base = ag_full[k].data_ptr()
             eng.set_snapshot_raw(slot, L, base, base + 8 * nfield, base + 16 * nfield, base + 24 * nfield, None, async_=async_)
+            ag_slot[k] = slot
             return
         h = ring[s % ring_n]
         eng.set_snapshot_raw(slot, L, h["zonal"].ctypes.data, h["merid"].ctypes.data, h["thick"].ctypes.data,
@@ -301,32 +404,53 @@ def main():
     upload(0, 0, False)
     upload(1, 1, False)
 
-    # seeds: uniform on the sphere |lat| < 80 deg, rank r keeps its longitude sector
+    # seeds: uniform on the sphere |lat| < 80 deg.  Sharding: the seed set is sorted along the mesh's
+    # Morton curve (each seed's cell from the engine's own point location, cells ranked along the curve) and cut into
+    # `world` equal contiguous blocks, so every rank gets the same count for ANY seed distribution and a spatially compact
+    # working set; `perm` is the caller-order index of each local seed (results scatter back by it).
     n_total = args.particles
     seeds_all = S.uniform_sphere_seeds(n_total, 20261018 + 5)
-    from mops_b200 import sharding
-    seeds_np, _global_idx = sharding.shard_seeds(seeds_all, rank, world)
+    if world > 1:
+        all_dev = torch.from_numpy(seeds_all).to(dev)
+        key = eng.morton_rank(all_dev)
+        order = torch.argsort(key, stable=True)
+        lo, hi = sharding.block_bounds(n_total, rank, world)
+        perm = order[lo:hi].contiguous()
+        seeds0 = all_dev[perm].contiguous()
+        del all_dev, key, order
+        torch.cuda.empty_cache()
+    else:
+        perm = None
+        seeds0 = torch.from_numpy(seeds_all).to(dev)
     del seeds_all
-    n = seeds_np.shape[0]
+    n = int(seeds0.shape[0])
     duration = DT * args.interval_steps
     record_t = min(3600, duration)  # hourly records
     each = duration // record_t
 
-    xyz = torch.from_numpy(seeds_np).to(dev)
+    xyz = seeds0.clone()
     depth = torch.full((n,), DEPTH, dtype=torch.float32, device=dev)
     out_pos = torch.empty((n, each, 3), dtype=torch.float64, device=dev)
     out_vel = torch.empty((n, each, 3), dtype=torch.float64, device=dev)
-    cfg = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, 0 if args.no_sort else 1)
+    sort = 0 if args.no_sort else 1
+    cfg = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, sort)
     io = capi.TrajIO(n, xyz.data_ptr(), depth.data_ptr(), None, out_pos.data_ptr(), out_vel.data_ptr(), None, None, None, None, None)
     counts = sharding.all_counts(n, world, device=dev)
     setup_s = time.perf_counter() - t_setup
 
+    def reset_particles():
+        if not args.chain:
+            xyz.copy_(seeds0)
+            depth.fill_(DEPTH)
+
     def one_step(i, io_, cfg_):
+        reset_particles()
         # next snapshot: async H2D + device preprocessing on the side stream (double buffering)
         upload((i + 2) % 3, i + 2, True)
         st = eng.traj_device(True, (i % 3, (i + 1) % 3), cfg_, io_, want_stats=True)
         if world > 1:
-            # the one exchange of the path: end points gathered to rank 0 over NCCL/NVLink
+            # the path's one exchange: end points gathered to rank 0 over NCCL/NVLink (the recorded trajectories follow the
+            # same route in the product's multi-GPU layer, mops_multi_*)
             sharding.gather_rows(xyz, counts, rank, world, dst=0)
         return st
 
@@ -334,10 +458,6 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def reset_particles():
-        xyz.copy_(torch.from_numpy(seeds_np))
-        depth.fill_(DEPTH)
 
     # ---- device-resident arm ---------------------------------------------------------------
     step_no = 0
@@ -360,9 +480,10 @@ def main():
         kern_steps.append(int(st.particle_steps))
     ev1.record()
     barrier()
-    launches = int(eng.info().total_launches) - launches0  # our kernels only (CUB sort passes not counted)
+    launches = int(eng.info().total_launches) - launches0  # our kernels only (CUB sort / select passes not counted)
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    ms_local = ms_total
     t = torch.tensor([ms_total, float(psteps)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -371,38 +492,54 @@ def main():
     else:
         psteps_all = float(psteps)
     value = psteps_all / (ms_total / 1e3)
+    executed_fraction = psteps_all / (float(n_total) * args.interval_steps * K)
 
-    # ---- e2e arm: same call with HOST (pinned) buffers --------------------------------------
+    # ---- e2e arm: the HOST-memory form (submit / wait, pinned buffers, two sets) ----------------
     e2e = None
     if not args.no_e2e:
-        h_xyz = pinned((n, 3)); h_xyz[...] = seeds_np
-        h_depth = torch.full((n,), DEPTH, dtype=torch.float32).pin_memory().numpy()
-        h_pos = pinned((n, each, 3)); h_vel = pinned((n, each, 3))
-        cfg_h = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_HOST, 0 if args.no_sort else 1)
-        io_h = capi.TrajIO(n, h_xyz.ctypes.data, h_depth.ctypes.data, None, h_pos.ctypes.data, h_vel.ctypes.data,
-                           None, None, None, None, None)
+        h_seeds = pinned((n, 3)); h_seeds[...] = seeds0.cpu().numpy()
+        h_seeds_t = torch.from_numpy(h_seeds)
+        cfg_h = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_HOST, sort)
+        sets = []
+        for _ in range(2):
+            hx = pinned((n, 3)); hd = pinned((n,), torch.float32); hp = pinned((n, each, 3)); hv = pinned((n, each, 3))
+            sets.append({"xyz": torch.from_numpy(hx), "depth": torch.from_numpy(hd), "keep": (hx, hd, hp, hv),
+                         "io": capi.TrajIO(n, hx.ctypes.data, hd.ctypes.data, None, hp.ctypes.data, hv.ctypes.data,
+                                           None, None, None, None, None)})
         h2d = n * 24 + n * 4
         d2h = n * 24 + n * 4 + 2 * n * each * 24
 
-        def e2e_step(i):
-            upload((i + 2) % 3, i + 2, True)
-            return eng.traj_device(True, (i % 3, (i + 1) % 3), cfg_h, io_h, want_stats=True)
+        def e2e_run(count):
+            """`count` steps, software-pipelined over the two host/staging sets; returns executed particle-steps"""
+            nonlocal step_no
+            tickets, ps = [], 0
+            for i in range(count):
+                k = i & 1
+                if i >= 2:
+                    ps += int(eng.traj_wait(tickets[i - 2], 1).particle_steps)  # set k is free again
+                hs = sets[k]
+                if not args.chain or i < 2:
+                    hs["xyz"].copy_(h_seeds_t); hs["depth"].fill_(DEPTH)        # this step's inputs, in host memory
+                else:
+                    eng.traj_wait(tickets[i - 1], 0)                            # chain: the previous step's end points
+                    hs["xyz"].copy_(sets[k ^ 1]["xyz"]); hs["depth"].copy_(sets[k ^ 1]["depth"])
+                upload((step_no + 2) % 3, step_no + 2, True)
+                tickets.append(eng.traj_submit(True, (step_no % 3, (step_no + 1) % 3), cfg_h, hs["io"]))
+                step_no += 1
+            for tk in tickets[max(0, count - 2):]:
+                ps += int(eng.traj_wait(tk, 1).particle_steps)
+            return ps
 
-        for _ in range(min(W, 2)):
-            e2e_step(step_no); step_no += 1
+        e2e_run(min(W, 2))
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ps = 0
-        for _ in range(K):
-            st = e2e_step(step_no); step_no += 1
-            ps += int(st.particle_steps)
+        ps = e2e_run(K)
         e1.record()
         barrier()
-        ms_e = e0.elapsed_time(e1)
         wall_e = (time.perf_counter() - t0) * 1e3
-        ms_e = max(ms_e, wall_e)  # host-side staging between calls counts too
+        ms_e = max(e0.elapsed_time(e1), wall_e)  # the copies run on the engine's own streams: the host-side wait is the clock
         te = torch.tensor([ms_e, float(ps)], dtype=torch.float64, device=dev)
         if world > 1:
             a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
@@ -411,76 +548,110 @@ def main():
         else:
             ps_all = float(ps)
         e2e = {"value": ps_all / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms_e / K}
+               "ms_per_step": ms_e / K,
+               "api": "mops_pathline_submit / mops_traj_wait (MOPS_MEM_HOST, pinned buffers, two staging sets)"}
+        del sets
 
-        if args.sweep_host_chunk:  # experiment: HOST-mode pipeline chunk size (particles; 0 = single pass)
-            for c in [int(x) for x in args.sweep_host_chunk.split(",")]:
-                os.environ["MOPS_HOST_CHUNK"] = str(c if c > 0 else 1 << 40)
-                e2e_step(step_no); step_no += 1
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                kk = 0.0
-                for _ in range(2):
-                    st = e2e_step(step_no); step_no += 1
-                    kk += st.kernel_ms
-                torch.cuda.synchronize()
-                if rank == 0:
-                    print(f"[sweep] host_chunk={c} ms_per_step={(time.perf_counter() - t0) * 500:.1f} kernel_ms={kk / 2:.1f}",
-                          file=sys.stderr, flush=True)
-            os.environ.pop("MOPS_HOST_CHUNK", None)
+    # ---- near-edge particles of this workload (diagnostic instantiation, outside the timed regions) -----------------
+    near_edge = None
+    if not args.no_secondary:
+        xyz.copy_(seeds0); depth.fill_(DEPTH)
+        cfg_e = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, sort, 1)
+        st_e = eng.traj_device(True, (step_no % 3, (step_no + 1) % 3), cfg_e, io, want_stats=True)
+        te = torch.tensor([float(st_e.near_edge_particles)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        near_edge = int(te[0])
 
-    # ---- roofline of the dominant kernel (k_advect<6,true>) ----------------------------------
-    peak, peak_src = load_peaks()
-    bps = algorithmic_bytes_per_step(L, True)
-    ach = [bps * s / (m / 1e3) / 1e9 for s, m in zip(kern_steps, kms) if m > 0]
-    achieved = float(np.mean(ach)) if ach else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("k_advect_pathline_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_advect<6,true>", "peak_source": peak_src,
-                "algorithmic_bytes_per_particle_step": bps, "kernel_ms_per_launch": float(np.mean(kms)),
-                "kernel_share_of_step": float(np.sum(kms)) / (ev0.elapsed_time(ev1) if world == 1 else ms_total),
-                "note": "logical bytes ignore L1/L2 reuse between particles sharing a cell; frac > 1 means the kernel is "
-                        "cache-/fp64-bound, not HBM-bound (profiles/README.md): dram_* is the real DRAM rate"}
-    if traffic and world == 1 and args.level == 9 and args.particles == 64_000_000 and args.interval_steps == 120 and kms:
-        # traffic.json is an ncu capture of exactly this launch shape (64 M particles x 120 steps, level-9 mesh)
-        roofline["dram_achieved"] = float(traffic) / (float(np.mean(kms)) / 1e3) / 1e9
-        roofline["dram_frac"] = roofline["dram_achieved"] / peak
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+    peak, peak_src, sm_max_mhz = load_peaks()
+    info = eng.info()
+    Kc = layer_levels_contract(L)
+    bps_contract = algorithmic_bytes_per_step(L, True, Kc)
+    bps_read = algorithmic_bytes_per_step(L, True, 2)  # the layer hint makes the kernel read K = 2 levels per vertex
+    kern_rate = [s / (m / 1e3) for s, m in zip(kern_steps, kms) if m > 0]
+    rate = float(np.mean(kern_rate)) if kern_rate else 0.0
+    prof = load_profile("k_advect_profile.json") or {}
+    same_shape = (world == 1 and args.level == 9 and args.particles == 64_000_000 and args.interval_steps == 120)
+    fp64_per_step = prof.get("fp64_thread_inst_per_particle_step")
+    fp64_peak = info.sm_count * 64 * sm_max_mhz * 1e6  # fp64 thread-instructions/s: 64 lanes per SM and clock (ncu: dfma peak_sustained)
+    traffic = prof.get("dram_bytes_per_launch") if same_shape else None
+    roofline = {
+        "bound": "fp64",
+        "achieved": (fp64_per_step * rate / 1e12) if fp64_per_step else None,
+        "peak": fp64_peak / 1e12,
+        "unit": "Tinst/s (fp64-pipe thread instructions; DFMA, DMUL, DADD, DSETP each take one slot)",
+        "frac": (fp64_per_step * rate / fp64_peak) if fp64_per_step else None,
+        "traffic": traffic,
+        "kernel": prof.get("kernel", "mops::k_advect<6,true,3,false,false,true,true>"),
+        "fp64_thread_inst_per_particle_step": fp64_per_step,
+        "fp64_source": prof.get("source"),
+        "peak_source": f"{info.sm_count} SMs x 64 fp64 lanes x {sm_max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json)",
+        "kernel_ms_per_launch": float(np.mean(kms)) if kms else None,
+        "kernel_particle_steps_per_s": rate,
+        "kernel_share_of_step": (float(np.sum(kms)) / ms_local) if kms else None,
+        "hbm": {
+            "note": "the contract's HBM roof (SURVEY 8d): logical bytes ignore L1/L2 reuse between the ~24 particles sharing a "
+                    "cell, so frac > 1 only says the kernel is not HBM-bound; dram_* is the real DRAM rate (ncu)",
+            "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "algorithmic_bytes_per_particle_step_contract": bps_contract, "contract_levels_per_vertex": Kc,
+            "achieved_contract": bps_contract * rate / 1e9, "frac_contract": bps_contract * rate / 1e9 / peak,
+            "algorithmic_bytes_per_particle_step_as_read": bps_read, "levels_per_vertex_as_read": 2,
+            "achieved_as_read": bps_read * rate / 1e9, "frac_as_read": bps_read * rate / 1e9 / peak,
+        },
+    }
+    if traffic and kms:
+        launches_per_step = prof.get("launches_per_step", 3)
+        roofline["hbm"]["dram_achieved"] = float(traffic) * launches_per_step / (float(np.mean(kms)) / 1e3) / 1e9
+        roofline["hbm"]["dram_frac"] = roofline["hbm"]["dram_achieved"] / peak
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
-    cpu = None
+    config = {"workload": workload, "particles_total": n_total, "particles_this_rank": n,
+              "cells": mesh.n_cells, "layers": L, "interval_steps": args.interval_steps,
+              "executed_fraction": executed_fraction,
+              "near_edge_particles": near_edge,
+              "l2_policy": "inputs larger than L2 (2 x 16.8 GB snapshots + particles); no flush needed",
+              "semantics": "reference (RK4 stages in the start-of-step cell; particles stop at their first failed stage)",
+              "sorted_particles": not args.no_sort, "setup_seconds": setup_s,
+              "mesh_bytes": int(info.mesh_bytes), "snapshot_bytes": int(info.snapshot_bytes[0]),
+              "parallelism": f"seeds sorted along the mesh's Morton curve and cut into {world} equal contiguous block(s), "
+                             "mesh+snapshots replicated",
+              "snapshot_distribution": ("1/N PCIe upload per rank + NCCL all-gather" if use_ag
+                                        else "whole snapshot uploaded by every rank")}
+    eng.close()
+    del xyz, depth, out_pos, out_vel, seeds0
+    torch.cuda.empty_cache()
+
+    # ---- CPU baseline + parity on its sample + remap figures (rank 0, N = 1 only) -----------------------------------
+    cpu = parity = remap = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            res = run_cpu_reference(args.cpu_level, L, 2_000_000, args.interval_steps, target_seconds=12.0)
+            res = run_cpu_reference(args.cpu_level, L, 2_000_000, args.interval_steps, target_seconds=12.0, keep_lines=True)
             cpu = {"value": res["particle_steps"] / float(np.mean(res["times"])), "unit": UNIT, "cores": res["cores"],
                    "kind": res["kind"], "sample": res["sample"]}
+            if not args.no_secondary:
+                parity, eng2 = parity_on_sample(res, local_rank)
+                try:
+                    remap = remap_secondary(eng2, res["mesh"], torch)
+                finally:
+                    eng2.close()
         except Exception as ex:  # the baseline is a reported number; never fail the bench on it
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {ex}"}
+            if cpu is None:
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {ex}"}
+            else:
+                parity = {"error": str(ex)}
 
     if rank == 0:
-        info = eng.info()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "particles_total": n_total, "particles_this_rank": n,
-                           "cells": mesh.n_cells, "layers": L, "interval_steps": args.interval_steps,
-                           "l2_policy": "inputs larger than L2 (2 x 16.8 GB snapshots + particles); no flush needed",
-                           "semantics": "reference (RK4 stages in the start-of-step cell; particles stop at their first failed stage)",
-                           "sorted_particles": not args.no_sort, "setup_seconds": setup_s,
-                           "mesh_bytes": int(info.mesh_bytes), "snapshot_bytes": int(info.snapshot_bytes[0]),
-                           "parallelism": f"particles sharded by longitude sector over {world} GPU(s), mesh+snapshots replicated",
-                           "snapshot_distribution": ("1/N PCIe upload per rank + NCCL all-gather" if use_ag
-                                                     else "whole snapshot uploaded by every rank")},
+                "dtype": "f64", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity_sample"] = parity
+        if remap is not None:
+            line["remap_pixels_per_s"] = remap
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -27,8 +27,9 @@
  *    cross this boundary in either direction are 0-based indices into the caller's cell
  *    arrays (what searchKDT returns); the engine's internal renumbering is invisible.
  *  - vec3 arrays are [n][3] doubles (the 24-byte layout of the reference's vec3).
- *  - `mem` selects whether particle / image buffers are HOST or DEVICE pointers.  Mesh and
- *    snapshot inputs are always host pointers (pinned memory makes their upload async).
+ *  - `mem` selects whether particle / image buffers are HOST or DEVICE pointers.  Mesh inputs are
+ *    host pointers; snapshot fields are host pointers (pinned memory makes their upload async) or
+ *    device pointers (see mops_side_wait_event).
  */
 #ifndef MOPS_B200_H
 #define MOPS_B200_H
@@ -190,15 +191,28 @@ typedef struct mops_traj_stats {
 } mops_traj_stats;
 
 /* Both calls integrate in launches of 40 steps (environment MOPS_SEGMENT_STEPS=<n>, 0 = one launch) with the
- * particles that stopped compacted away between launches -- results are identical either way.  Between launches the
- * host reads back the live count, so a call with more steps than one launch has synchronised with the stream before
- * it returns; calls that fit one launch and pass stats = NULL stay asynchronous with MOPS_MEM_DEVICE buffers. */
+ * particles that stopped compacted away between launches -- results are identical either way.  The live count stays
+ * on the device, so MOPS_MEM_DEVICE calls with stats = NULL are asynchronous on the context's stream whatever their
+ * length.  MOPS_MEM_HOST calls stage through device scratch and complete before they return; their asynchronous
+ * form is submit / wait below. */
 /* replaces MOPS::Factory::StreamLine (src/Common/MOPSFactory.h:28-33 -> VK:653-1015) */
 int mops_streamline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io,
                     mops_traj_stats* stats);
 /* replaces MOPS::Factory::PathLine (src/Common/MOPSFactory.h:35-40 -> VK:1017-1496) */
 int mops_pathline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot,
                   const mops_traj_io* io, mops_traj_stats* stats);
+
+/* Asynchronous HOST-memory form (no counterpart in the reference, whose wrappers block: VK:1005-1014).  submit copies the
+ * seeds up on a copy stream, enqueues the kernels and the copy-back (end points first, then the recorded trajectories) on a
+ * second copy stream, and returns a ticket; two device staging sets alternate, so a second submit before the first wait
+ * overlaps its H2D and the first call's D2H with the kernels (at most two tickets are in flight: a third submit first
+ * completes the oldest).  The io buffers must stay valid (and should be pinned, mops_host_alloc) until the wait.
+ * mops_traj_wait(what = 0) returns once io.xyz / io.depth hold the end points (what the next interval of a chain needs),
+ * what = 1 once every output has landed; stats (may be NULL) are filled by the what = 1 wait. */
+int mops_streamline_submit(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io, int64_t* ticket);
+int mops_pathline_submit(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot,
+                         const mops_traj_io* io, int64_t* ticket);
+int mops_traj_wait(mops_ctx* ctx, int64_t ticket, int32_t what, mops_traj_stats* stats);
 
 /* host-side line assembly + NaN trimming (src/Common/TrajectoryCommon.h:43-190; R7, R8):
  * raw [n][each][3] -> points / velocity [n][each+1][3], temperature / salinity [n][each+1]

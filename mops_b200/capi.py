@@ -29,7 +29,8 @@ STATUS_NAMES = {0: "alive", 1: "bad_cell", 2: "not_in_cell", 3: "bad_column", 4:
 ABI_SYMBOLS = [
     "mops_abi_version", "mops_create", "mops_destroy", "mops_last_error", "mops_host_alloc", "mops_host_free",
     "mops_synchronize", "mops_set_stream", "mops_mark", "mops_elapsed_ms", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait", "mops_side_wait_event",
-    "mops_get_prepared", "mops_locate", "mops_streamline", "mops_pathline", "mops_finalize_lines",
+    "mops_get_prepared", "mops_locate", "mops_streamline", "mops_pathline", "mops_streamline_submit", "mops_pathline_submit",
+    "mops_traj_wait", "mops_finalize_lines",
     "mops_remap_fixed_depth", "mops_remap_fixed_layer", "mops_regrid_fixed_latitude", "mops_get_info",
 ]
 
@@ -111,6 +112,9 @@ def load_library():
     lib.mops_locate.argtypes = [vp, i32, i64, vp, vp]
     lib.mops_streamline.argtypes = [vp, C.POINTER(TrajCfg), i32, C.POINTER(TrajIO), C.POINTER(TrajStats)]
     lib.mops_pathline.argtypes = [vp, C.POINTER(TrajCfg), i32, i32, C.POINTER(TrajIO), C.POINTER(TrajStats)]
+    lib.mops_streamline_submit.argtypes = [vp, C.POINTER(TrajCfg), i32, C.POINTER(TrajIO), C.POINTER(i64)]
+    lib.mops_pathline_submit.argtypes = [vp, C.POINTER(TrajCfg), i32, i32, C.POINTER(TrajIO), C.POINTER(i64)]
+    lib.mops_traj_wait.argtypes = [vp, i64, i32, C.POINTER(TrajStats)]
     lib.mops_finalize_lines.argtypes = [i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.mops_remap_fixed_depth.argtypes = [vp, C.POINTER(RemapCfg), i32, vp, vp, vp, C.POINTER(RemapStats)]
     lib.mops_remap_fixed_layer.argtypes = [vp, C.POINTER(ViewCfg), i32, vp, vp, C.POINTER(RemapStats)]
@@ -296,6 +300,22 @@ class Engine:
             rc = self.lib.mops_streamline(self.h, C.byref(cfg), slots[0], C.byref(io), sp)
         self._ck(rc)
         return st if want_stats else None
+
+    def traj_submit(self, path, slots, cfg: TrajCfg, io: TrajIO) -> int:
+        """asynchronous HOST-memory call (cfg.mem = MEM_HOST, pinned buffers): returns a ticket for traj_wait"""
+        tk = C.c_int64(0)
+        if path:
+            rc = self.lib.mops_pathline_submit(self.h, C.byref(cfg), slots[0], slots[1], C.byref(io), C.byref(tk))
+        else:
+            rc = self.lib.mops_streamline_submit(self.h, C.byref(cfg), slots[0], C.byref(io), C.byref(tk))
+        self._ck(rc)
+        return tk.value
+
+    def traj_wait(self, ticket: int, what: int = 1, want_stats=True) -> Optional[TrajStats]:
+        """what = 0: end points (io.xyz / io.depth) have landed; what = 1: every output has (stats filled)"""
+        st = TrajStats()
+        self._ck(self.lib.mops_traj_wait(self.h, C.c_int64(ticket), what, C.byref(st) if (want_stats and what == 1) else None))
+        return st if (want_stats and what == 1) else None
 
     def finalize_lines(self, seeds, raw_pos, raw_vel, pathline_mode=False):
         n, each = raw_pos.shape[0], raw_pos.shape[1]

@@ -6,6 +6,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +32,8 @@ struct Snapshot {
     double4* velw = nullptr;
     double* attr[MOPS_MAX_ATTRS] = {nullptr, nullptr};
     unsigned char* mono = nullptr;
+    bool has_w = false;   // some velw record has a w component other than +0.0 (vertVelocityTop given and not all zero)
+    bool w_known = true;  // false: async upload in flight, the device flag has not been read back yet
     int nonmono = 0;
     size_t bytes = 0;
     cudaEvent_t ready = nullptr;    // recorded on the side stream after preprocessing
@@ -73,22 +77,29 @@ struct mops_ctx {
     // staging for snapshot upload (caller cell order), reused by every snapshot on the side stream
     Buf st_zonal, st_merid, st_thick, st_wtop, st_bottom, st_ztopc, st_attr, st_vmono;
     int* d_nonmono = nullptr;
+    int* d_anyw = nullptr;  // [slot] set by k_vertex_fields when a prepared vertical velocity is not +0.0
     // particle scratch (host-memory mode) + sort scratch
-    Buf p_xyz, p_depth, p_cell0, p_cell_int, p_out_pos, p_out_vel, p_out_attr, p_log, p_status, p_steps, p_fcell, p_edge;
+    Buf p_xyz, p_cell0, p_cell_int; // mops_locate (HOST) staging, internal start cells
     Buf s_keys, s_vals, s_keys2, s_vals2, s_tmp;
     Buf s_state;            // AdvState[n]: parked loop state of the compacting multi-launch form
-    int* d_nsel = nullptr;  // number of live particles after a compaction
+    int* d_nsel = nullptr;  // [2] number of live particles after a compaction (ping-pong: read by the next launch / compaction)
     int segment_steps = 40; // steps per launch of the compacting form; MOPS_SEGMENT_STEPS overrides (0 = one launch per call)
     Buf r_img0, r_img1, r_cells;
     unsigned long long* counters = nullptr; // [4]
-    // HOST-mode pipeline (large n): two sets of chunk-sized scratch so that the H2D of chunk k+1 and the D2H
-    // of chunk k-1 overlap the kernel of chunk k
-    struct PipeSet {
-        Buf xyz, depth, cell0, cell_int, vals, vals2, keys2, tmp, out_pos, out_vel, out_attr, log, status, steps, fcell, edge;
-        cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
-    } pipe[2];
+    // HOST-mode trajectory calls: two sets of device staging + events, used alternately, so that the H2D of call k+1
+    // (copy_in stream) and the D2H of call k (copy_out stream) overlap the kernels of the other call on the main stream
+    struct HostSet {
+        Buf xyz, depth, cell0, out_pos, out_vel, out_attr, log, status, steps, fcell, edge;
+        unsigned long long* d_counters = nullptr; // [4] device
+        unsigned long long* h_counters = nullptr; // [4] pinned host
+        cudaEvent_t begin = nullptr, in_done = nullptr, loc0 = nullptr, loc1 = nullptr, k0 = nullptr, k1 = nullptr, ends_done = nullptr,
+                    out_done = nullptr;
+        bool busy = false;       // a submitted call has not been waited for yet
+        long long ticket = 0;    // its ticket
+        long long launches = 0;  // kernels it launched
+    } hset[2];
+    long long host_seq = 0;      // tickets issued so far
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    std::vector<cudaEvent_t> chunk_ev; // (kernel start, kernel end) pairs, grown on demand
     // kd-tree over the cell centres, only for meshes with removed cells (see kd_nearest)
     double4* kd_pts = nullptr;
     unsigned char* kd_dim = nullptr;
@@ -272,6 +283,21 @@ int wait_slot(mops_ctx* ctx, int slot)
     return MOPS_OK;
 }
 
+// a vertVelocityTop array was given with an asynchronous upload: read back whether it held anything but +0.0 (the upload
+// of a slot that a trajectory call is about to use was enqueued a whole interval earlier, so this does not stall in a
+// double-buffered chain)
+int resolve_w(mops_ctx* ctx, int slot)
+{
+    Snapshot& s = ctx->snap[slot];
+    if (s.w_known) return MOPS_OK;
+    CK(cudaEventSynchronize(s.ready));
+    int any = 1;
+    CK(cudaMemcpy(&any, ctx->d_anyw + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    s.has_w = any != 0;
+    s.w_known = true;
+    return MOPS_OK;
+}
+
 int mark_use(mops_ctx* ctx, int slot)
 {
     Snapshot& s = ctx->snap[slot];
@@ -325,6 +351,8 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
         }
     }
     s.L = L;
+    s.has_w = (wtop != nullptr);
+    s.w_known = (wtop == nullptr);
     s.n_attr = n_attr;
     s.n_attr_total = n_attr_total;
 
@@ -351,11 +379,12 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
     CK(cudaMemcpyAsync(ctx->st_bottom.p, bottom, nC * 8, kind_of(bottom), st));
     if (wtop) CK(cudaMemcpyAsync(ctx->st_wtop.p, wtop, nC * (L + 1) * 8, kind_of(wtop), st));
 
+    CK(cudaMemsetAsync(ctx->d_anyw + slot, 0, sizeof(int), st));
     k_cell_ztop<<<blocks_for(ctx->nC, 128), 128, 0, st>>>((const double*)ctx->st_thick.p, (const double*)ctx->st_bottom.p,
                                                           (double*)ctx->st_ztopc.p, ctx->nC, L);
     k_vertex_fields<<<blocks_for((long long)nV * L, 256), 256, 0, st>>>(
         ctx->vert, ctx->vcell_ext, ctx->trig, (const double*)ctx->st_ztopc.p, (const double*)ctx->st_zonal.p,
-        (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L);
+        (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L, ctx->d_anyw + slot);
     ctx->launches += 2;
     for (int a = 0; a < n_attr; ++a) {
         CK(cudaMemcpyAsync(ctx->st_attr.p, attrs[a], nC * L * 8, kind_of(attrs[a]), st));
@@ -379,6 +408,12 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
     if (!async) {
         CK(cudaStreamSynchronize(st));
         CK(cudaMemcpy(&s.nonmono, ctx->d_nonmono + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!s.w_known) {
+            int any = 1;
+            CK(cudaMemcpy(&any, ctx->d_anyw + slot, sizeof(int), cudaMemcpyDeviceToHost));
+            s.has_w = any != 0;
+            s.w_known = true;
+        }
         s.pending = false;
     } else {
         s.nonmono = -1;
@@ -416,41 +451,45 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
 // does not pay registers for either.  Resident 128-thread blocks per SM (register budget 65536 / (128 * MINB)):
 // 3 for the 6- and 8-wide records, 1 for the 20-wide ones -- from measurements on B200 (profiles/README.md:
 // 2 blocks 990 ms, 3 blocks 817 ms, 4 blocks 855 ms, 5 blocks 1065 ms, 6 blocks 1298 ms on the same step).
-template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false>
+template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false, bool NOW = false>
 void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 {
     const int grid = blocks_for(P.n, MOPS_ADV_BLOCK);
-    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR, SEG><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
+    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR, SEG, NOW><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
     ctx->launches++;
 }
 
-// seg = true: a segment of a compacting multi-launch call (never combined with the EXTRA instantiations)
+// Production launches always use the SEG instantiation (a single launch is the segment [0, times) with no parked state), the
+// EXTRA instantiations (walk semantics / near-edge diagnostic) are single-launch only.  now = neither snapshot carries
+// vertVelocityTop: hexagonal meshes (M == 6) then run the instantiation that does not accumulate the vertical sums.
 template <int M>
-void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool seg = false)
+void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool now)
 {
     const bool extra = P.walk || P.diag_edge;
     const bool attr = path && P.attr_count > 0 && P.out_attr;
+    constexpr bool HEX = (M == 6);
     if (!path) {
         if (extra) launch_advect_inst<M, false, true, false>(ctx, P);
-        else if (seg) launch_advect_inst<M, false, false, false, true>(ctx, P);
-        else launch_advect_inst<M, false, false, false>(ctx, P);
+        else if (HEX && now) launch_advect_inst<M, false, false, false, true, HEX>(ctx, P);
+        else launch_advect_inst<M, false, false, false, true>(ctx, P);
     } else if (attr) {
         if (extra) launch_advect_inst<M, true, true, true>(ctx, P);
-        else if (seg) launch_advect_inst<M, true, false, true, true>(ctx, P);
-        else launch_advect_inst<M, true, false, true>(ctx, P);
+        else if (HEX && now) launch_advect_inst<M, true, false, true, true, HEX>(ctx, P);
+        else launch_advect_inst<M, true, false, true, true>(ctx, P);
     } else {
         if (extra) launch_advect_inst<M, true, true, false>(ctx, P);
-        else if (seg) launch_advect_inst<M, true, false, false, true>(ctx, P);
-        else launch_advect_inst<M, true, false, false>(ctx, P);
+        else if (HEX && now) launch_advect_inst<M, true, false, false, true, HEX>(ctx, P);
+        else launch_advect_inst<M, true, false, false, true>(ctx, P);
     }
 }
 
-void dispatch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool seg)
+void dispatch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
+    const bool now = P.no_w != 0;
     switch (ctx->M) {
-    case 6: launch_advect<6>(ctx, P, path, seg); break;
-    case 8: launch_advect<8>(ctx, P, path, seg); break;
-    default: launch_advect<20>(ctx, P, path, seg); break;
+    case 6: launch_advect<6>(ctx, P, path, now); break;
+    case 8: launch_advect<8>(ctx, P, path, now); break;
+    default: launch_advect<20>(ctx, P, path, now); break;
     }
 }
 
@@ -487,7 +526,7 @@ int run_range(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, long long m, c
         d_order = (const int*)vals2.p;
     }
     P.n = m; P.order = d_order; P.cell0 = d_cell_int;
-    P.step_begin = 0; P.step_end = P.times; P.state = nullptr;
+    P.step_begin = 0; P.step_end = P.times; P.state = nullptr; P.n_live = nullptr;
     if (ev_k0) CK(cudaEventRecord(ev_k0, st));
     const int seg = ctx->segment_steps;
     if (seg > 0 && P.times > seg && !(P.walk || P.diag_edge)) {
@@ -507,140 +546,74 @@ int run_range(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, long long m, c
             ctx->launches++;
         }
         P.state = (AdvState*)ctx->s_state.p;
-        long long live = m;
-        for (int b = 0; b < P.times && live > 0; b += seg) {
+        // The live count stays on the device (d_nsel[0/1], written by one compaction and read by the next launch and the
+        // next compaction): every launch is sized for all m positions and lanes beyond the live prefix exit at once, so the
+        // host never waits for a segment and the whole call is stream-asynchronous (and graph-capturable).
+        const int* n_live = nullptr;
+        int flip = 0;
+        for (int b = 0; b < P.times; b += seg) {
             const int e = std::min(P.times, b + seg);
-            P.n = live; P.order = cur; P.step_begin = b; P.step_end = e;
-            dispatch_advect(ctx, P, path, true);
+            P.n = m; P.order = cur; P.step_begin = b; P.step_end = e; P.n_live = n_live;
+            dispatch_advect(ctx, P, path);
             CK(cudaGetLastError());
             if (e < P.times) {
                 size_t tmp_bytes = 0;
-                const AdvAliveOp op{P.state};
-                cub::DeviceSelect::If(nullptr, tmp_bytes, (const int*)cur, nxt, ctx->d_nsel, (int)live, op, st);
+                const AdvAliveFlag op{cur, P.state, n_live};
+                cub::TransformInputIterator<bool, AdvAliveFlag, cub::CountingInputIterator<int>> flags(cub::CountingInputIterator<int>(0), op);
+                int* n_out = ctx->d_nsel + flip;
+                cub::DeviceSelect::Flagged(nullptr, tmp_bytes, (const int*)cur, flags, nxt, n_out, (int)m, st);
                 if ((rc = ensure(ctx, tmp, tmp_bytes))) return rc;
-                CK(cub::DeviceSelect::If(tmp.p, tmp_bytes, (const int*)cur, nxt, ctx->d_nsel, (int)live, op, st));
-                int h_live = 0;
-                CK(cudaMemcpyAsync(&h_live, ctx->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                live = h_live;
+                CK(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, (const int*)cur, flags, nxt, n_out, (int)m, st));
+                n_live = n_out;
+                flip ^= 1;
                 std::swap(cur, nxt);
             }
         }
     } else {
-        dispatch_advect(ctx, P, path, false);
+        dispatch_advect(ctx, P, path);
         CK(cudaGetLastError());
     }
     if (ev_k1) CK(cudaEventRecord(ev_k1, st));
     return MOPS_OK;
 }
 
-// HOST-mode call on many particles: caller-order chunks are software-pipelined over three streams -- H2D of
-// chunk k+1 and D2H of chunk k-1 overlap the kernel of chunk k (also with pageable buffers, because the
-// blocking D2H of chunk k-1 is issued after the kernel of chunk k has been enqueued).
-int trajectory_host_pipelined(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, const mops_traj_io* io, mops_traj_stats* stats,
-                              AdvectParams P0, int each, int times, bool want_attr, long long chunk, long long launches0)
+// wait for a submitted HOST-mode call: what = 0 -> its end points / depths have landed in io.xyz / io.depth,
+// what = 1 -> every output has; stats are filled when the whole call is complete
+int host_wait(mops_ctx* ctx, long long ticket, int what, mops_traj_stats* stats)
 {
-    const long long n = io->n;
-    const int nchunks = (int)((n + chunk - 1) / chunk);
-    cudaStream_t st = ctx->stream;
-    int rc;
-    while ((int)ctx->chunk_ev.size() < 2 * nchunks) {
-        cudaEvent_t e;
-        CK(cudaEventCreate(&e));
-        ctx->chunk_ev.push_back(e);
-    }
-    for (auto& S : ctx->pipe) {
-        if ((rc = ensure(ctx, S.xyz, (size_t)chunk * 24))) return rc;
-        if ((rc = ensure(ctx, S.depth, (size_t)chunk * 4))) return rc;
-        if ((rc = ensure(ctx, S.cell_int, (size_t)chunk * 4))) return rc;
-        if (io->cell0 && (rc = ensure(ctx, S.cell0, (size_t)chunk * 4))) return rc;
-        if ((rc = ensure(ctx, S.out_pos, (size_t)chunk * each * 24))) return rc;
-        if ((rc = ensure(ctx, S.out_vel, (size_t)chunk * each * 24))) return rc;
-        if (want_attr && (rc = ensure(ctx, S.out_attr, (size_t)chunk * each * 24))) return rc;
-        if (io->out_cell_log && (rc = ensure(ctx, S.log, (size_t)chunk * times * 4))) return rc;
-        if (io->out_status && (rc = ensure(ctx, S.status, (size_t)chunk * 4))) return rc;
-        if (io->out_steps && (rc = ensure(ctx, S.steps, (size_t)chunk * 4))) return rc;
-        if (io->out_cell && (rc = ensure(ctx, S.fcell, (size_t)chunk * 4))) return rc;
-        if (io->out_min_edge && (rc = ensure(ctx, S.edge, (size_t)chunk * 8))) return rc;
-    }
-    CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
-    // the copy streams start after everything already queued on the compute stream
-    CK(cudaEventRecord(ctx->ev1, st));
-    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev1, 0));
-    CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev1, 0));
-
-    auto copy_out = [&](int k) -> int {
-        auto& S = ctx->pipe[k & 1];
-        const long long lo = (long long)k * chunk, m = std::min(chunk, n - lo);
-        cudaStream_t so = ctx->copy_out;
-        CK(cudaStreamWaitEvent(so, S.k_done, 0));
-        CK(cudaMemcpyAsync(io->xyz + 3 * lo, S.xyz.p, (size_t)m * 24, cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(io->depth + lo, S.depth.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(io->out_pos + lo * each * 3, S.out_pos.p, (size_t)m * each * 24, cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(io->out_vel + lo * each * 3, S.out_vel.p, (size_t)m * each * 24, cudaMemcpyDeviceToHost, so));
-        if (want_attr) CK(cudaMemcpyAsync(io->out_attr + lo * each * 3, S.out_attr.p, (size_t)m * each * 24, cudaMemcpyDeviceToHost, so));
-        if (io->out_cell_log) CK(cudaMemcpyAsync(io->out_cell_log + lo * times, S.log.p, (size_t)m * times * 4, cudaMemcpyDeviceToHost, so));
-        if (io->out_status) CK(cudaMemcpyAsync(io->out_status + lo, S.status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
-        if (io->out_steps) CK(cudaMemcpyAsync(io->out_steps + lo, S.steps.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
-        if (io->out_cell) CK(cudaMemcpyAsync(io->out_cell + lo, S.fcell.p, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
-        if (io->out_min_edge) CK(cudaMemcpyAsync(io->out_min_edge + lo, S.edge.p, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
-        CK(cudaEventRecord(S.out_done, so));
+    mops_ctx::HostSet& S = ctx->hset[ticket & 1];
+    if (ticket <= 0 || ticket > ctx->host_seq) return fail(ctx, MOPS_E_INVALID, "unknown ticket %lld", ticket);
+    if (S.ticket != ticket) { // already completed (and its staging set reused) -- nothing left to wait for
+        if (stats) std::memset(stats, 0, sizeof(*stats));
         return MOPS_OK;
-    };
-
-    for (int k = 0; k < nchunks; ++k) {
-        auto& S = ctx->pipe[k & 1];
-        const long long lo = (long long)k * chunk, m = std::min(chunk, n - lo);
-        cudaStream_t si = ctx->copy_in;
-        if (k >= 2) CK(cudaStreamWaitEvent(si, S.out_done, 0)); // set free again: chunk k-2 has been copied out
-        CK(cudaMemcpyAsync(S.xyz.p, io->xyz + 3 * lo, (size_t)m * 24, cudaMemcpyHostToDevice, si));
-        CK(cudaMemcpyAsync(S.depth.p, io->depth + lo, (size_t)m * 4, cudaMemcpyHostToDevice, si));
-        if (io->cell0) CK(cudaMemcpyAsync(S.cell0.p, io->cell0 + lo, (size_t)m * 4, cudaMemcpyHostToDevice, si));
-        CK(cudaEventRecord(S.in_done, si));
-
-        CK(cudaStreamWaitEvent(st, S.in_done, 0));
-        if (k >= 2) CK(cudaStreamWaitEvent(st, S.out_done, 0));
-        if (io->out_cell_log) CK(cudaMemsetAsync(S.log.p, 0xff, (size_t)m * times * 4, st));
-        AdvectParams P = P0;
-        P.pos = (double*)S.xyz.p; P.depth = (float*)S.depth.p;
-        P.out_pos = (double*)S.out_pos.p; P.out_vel = (double*)S.out_vel.p; P.out_attr = want_attr ? (double*)S.out_attr.p : nullptr;
-        P.cell_log = io->out_cell_log ? (int*)S.log.p : nullptr;
-        P.status = io->out_status ? (int*)S.status.p : nullptr;
-        P.steps = io->out_steps ? (int*)S.steps.p : nullptr;
-        P.fcell = io->out_cell ? (int*)S.fcell.p : nullptr;
-        P.min_edge = io->out_min_edge ? (double*)S.edge.p : nullptr;
-        P.diag_edge = (cfg->count_near_edge || P.min_edge) ? 1 : 0;
-        if ((rc = run_range(ctx, cfg, path, m, io->cell0 ? (const int*)S.cell0.p : nullptr, (int*)S.cell_int.p, S.vals, S.vals2, S.keys2,
-                            S.tmp, P, nullptr, nullptr, ctx->chunk_ev[2 * k], ctx->chunk_ev[2 * k + 1])))
-            return rc;
-        CK(cudaEventRecord(S.k_done, st));
-        if (k >= 1 && (rc = copy_out(k - 1))) return rc;
     }
-    if ((rc = copy_out(nchunks - 1))) return rc;
-    CK(cudaStreamWaitEvent(st, ctx->pipe[0].out_done, 0));
-    if (nchunks > 1) CK(cudaStreamWaitEvent(st, ctx->pipe[1].out_done, 0));
-    unsigned long long h_counters[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev_end, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaSetDevice(ctx->device));
+    if (what == 0) {
+        CK(cudaEventSynchronize(S.ends_done));
+        return MOPS_OK;
+    }
+    CK(cudaEventSynchronize(S.out_done));
+    S.busy = false;
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
-        stats->particle_steps = (int64_t)h_counters[0];
-        stats->alive_at_end = (int64_t)h_counters[1];
-        stats->near_edge_particles = (int64_t)h_counters[3];
+        stats->particle_steps = (int64_t)S.h_counters[0];
+        stats->alive_at_end = (int64_t)S.h_counters[1];
+        stats->near_edge_particles = (int64_t)S.h_counters[3];
         float ms = 0.f;
-        for (int k = 0; k < nchunks; ++k)
-            if (cudaEventElapsedTime(&ms, ctx->chunk_ev[2 * k], ctx->chunk_ev[2 * k + 1]) == cudaSuccess) stats->kernel_ms += ms;
-        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_end) == cudaSuccess) stats->total_ms = ms;
-        stats->launches = (int32_t)(ctx->launches - launches0);
+        if (cudaEventElapsedTime(&ms, S.k0, S.k1) == cudaSuccess) stats->kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, S.loc0, S.loc1) == cudaSuccess) stats->locate_ms = ms;
+        if (cudaEventElapsedTime(&ms, S.begin, S.out_done) == cudaSuccess) stats->total_ms = ms;
+        stats->launches = (int32_t)S.launches;
     }
     return MOPS_OK;
 }
 
+// ticket != nullptr: HOST-mode submit -- returns once everything is enqueued; host_wait completes it.
 int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back, const mops_traj_io* io, mops_traj_stats* stats,
-                    bool path)
+                    bool path, long long* ticket)
 {
     if (!ctx) return MOPS_E_INVALID;
+    if (ticket) *ticket = 0;
     if (!cfg || !io) return fail(ctx, MOPS_E_INVALID, "null cfg/io");
     if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "no mesh");
     if (front < 0 || front >= MOPS_MAX_SNAPSHOT_SLOTS || !ctx->snap[front].valid) return fail(ctx, MOPS_E_STATE, "snapshot slot %d not set", front);
@@ -654,6 +627,8 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     const int each = (int)(cfg->duration / cfg->record_t);
     const int times = (int)(cfg->duration / cfg->delta_t);
     if (each <= 0 || times <= 0) return fail(ctx, MOPS_E_INVALID, "invalid integration steps"); // VK:709-712
+    const bool host = (cfg->mem == MOPS_MEM_HOST);
+    if (ticket && !host) return fail(ctx, MOPS_E_INVALID, "submit/wait is the HOST-memory form; DEVICE-memory calls are asynchronous on the context's stream already");
     if (n == 0) {
         if (stats) std::memset(stats, 0, sizeof(*stats));
         return MOPS_OK;
@@ -666,11 +641,11 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     int rc;
     if ((rc = wait_slot(ctx, front))) return rc;
     if (path && (rc = wait_slot(ctx, back))) return rc;
+    if ((rc = resolve_w(ctx, front))) return rc;
+    if (path && (rc = resolve_w(ctx, back))) return rc;
 
-    const bool host = (cfg->mem == MOPS_MEM_HOST);
     const long long launches0 = ctx->launches;
     cudaStream_t st = ctx->stream;
-    CK(cudaEventRecord(ctx->ev0, st));
 
     // pathline attributes: only when the front snapshot holds more than one (VK:1093-1104)
     int attr_count = 0;
@@ -682,136 +657,119 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     P.rec = ctx->rec; P.c4 = ctx->c4; P.c_int2ext = ctx->c_int2ext; P.nC = ctx->nC; P.L = F.L;
     P.sv[0] = view_of(F); P.sv[1] = view_of(B);
     P.attr_count = attr_count;
+    P.no_w = (!F.has_w && !B.has_w) ? 1 : 0;
     P.use_euler = (cfg->method == MOPS_METHOD_EULER) ? 1 : 0;
     P.delta_t = (cfg->direction == MOPS_DIR_FORWARD ? 1 : -1) * (int)cfg->delta_t;
     P.times = times; P.each = each; P.record_t = (int)cfg->record_t;
     P.record_interval = (int)(cfg->record_t / cfg->delta_t);
     P.duration = (double)cfg->duration;
     P.walk = (cfg->semantics == MOPS_SEM_WALK) ? 1 : 0;
-    P.counters = ctx->counters;
-
-    // HOST-mode calls, opt-in (MOPS_HOST_CHUNK=<particles>): chunked three-stream pipeline, copies overlap
-    // the kernels.  Chunks are caller-order ranges (results must land in caller order), so it only pays when
-    // the caller's seeds are already spatially coherent: with the bench's uniformly random 64 M seeds a 4 M
-    // chunk has 1.5 particles per cell instead of 24 and the kernels slow down by more than the copies cost
-    // (B200, per step: single pass 3.49 s; 16 M chunks 4.07 s; 8 M 4.81 s; 4 M 6.03 s; 2 M 7.87 s), hence off
-    // by default.
-    {
-        long long chunk = 0;
-        if (const char* e = getenv("MOPS_HOST_CHUNK")) chunk = atoll(e);
-        if (host && chunk > 0 && n > chunk && !getenv("MOPS_ZERO_COPY")) {
-            rc = trajectory_host_pipelined(ctx, cfg, path, io, stats, P, each, times, want_attr, chunk, launches0);
-            if (rc) return rc;
-            if ((rc = mark_use(ctx, front))) return rc;
-            if (path && back != front && (rc = mark_use(ctx, back))) return rc;
-            return MOPS_OK;
-        }
-    }
 
     const size_t out_bytes = (size_t)n * each * 3 * sizeof(double);
-    double *d_xyz, *d_out_pos, *d_out_vel, *d_out_attr = nullptr;
-    float* d_depth;
-    int *d_log = nullptr, *d_status = nullptr, *d_steps = nullptr, *d_fcell = nullptr;
-    double* d_edge = nullptr;
-    const int* d_cell0_ext = nullptr;
-    // HOST mode: outputs are staged in device scratch and copied back with cudaMemcpyAsync.  Opt-in
-    // experiment (MOPS_ZERO_COPY=1, pinned UVA-mapped buffers): the kernel writes its records straight into
-    // host memory over PCIe.  Measured on B200 it is a loss -- 24-byte scattered stores become tiny PCIe
-    // writes: 8.3 s per bench step instead of 3.4 s staged -- so it is off by default.
-    auto mapped = [](void* p) -> void* {
-        if (!p) return nullptr;
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        return (a.type == cudaMemoryTypeHost && a.devicePointer) ? a.devicePointer : nullptr;
-    };
-    bool zero_copy_out = false;
-    if (host) {
-        if ((rc = ensure(ctx, ctx->p_xyz, (size_t)n * 24))) return rc;
-        if ((rc = ensure(ctx, ctx->p_depth, (size_t)n * 4))) return rc;
-        d_xyz = (double*)ctx->p_xyz.p; d_depth = (float*)ctx->p_depth.p;
-        void* mp = mapped(io->out_pos);
-        void* mv = mapped(io->out_vel);
-        void* ma = want_attr ? mapped(io->out_attr) : nullptr;
-        zero_copy_out = mp && mv && (!want_attr || ma) && getenv("MOPS_ZERO_COPY") != nullptr;
-        if (zero_copy_out) {
-            d_out_pos = (double*)mp; d_out_vel = (double*)mv;
-            if (want_attr) d_out_attr = (double*)ma;
-        } else {
-            if ((rc = ensure(ctx, ctx->p_out_pos, out_bytes))) return rc;
-            if ((rc = ensure(ctx, ctx->p_out_vel, out_bytes))) return rc;
-            d_out_pos = (double*)ctx->p_out_pos.p; d_out_vel = (double*)ctx->p_out_vel.p;
-        }
-        CK(cudaMemcpyAsync(d_xyz, io->xyz, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_depth, io->depth, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        if (io->cell0) {
-            if ((rc = ensure(ctx, ctx->p_cell0, (size_t)n * 4))) return rc;
-            CK(cudaMemcpyAsync(ctx->p_cell0.p, io->cell0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-            d_cell0_ext = (const int*)ctx->p_cell0.p;
-        }
-        if (want_attr && !zero_copy_out) { if ((rc = ensure(ctx, ctx->p_out_attr, out_bytes))) return rc; d_out_attr = (double*)ctx->p_out_attr.p; }
-        if (io->out_cell_log) { if ((rc = ensure(ctx, ctx->p_log, (size_t)n * times * 4))) return rc; d_log = (int*)ctx->p_log.p; }
-        if (io->out_status) { if ((rc = ensure(ctx, ctx->p_status, (size_t)n * 4))) return rc; d_status = (int*)ctx->p_status.p; }
-        if (io->out_steps) { if ((rc = ensure(ctx, ctx->p_steps, (size_t)n * 4))) return rc; d_steps = (int*)ctx->p_steps.p; }
-        if (io->out_cell) { if ((rc = ensure(ctx, ctx->p_fcell, (size_t)n * 4))) return rc; d_fcell = (int*)ctx->p_fcell.p; }
-        if (io->out_min_edge) { if ((rc = ensure(ctx, ctx->p_edge, (size_t)n * 8))) return rc; d_edge = (double*)ctx->p_edge.p; }
-    } else {
-        d_xyz = io->xyz; d_depth = io->depth; d_out_pos = io->out_pos; d_out_vel = io->out_vel;
-        d_out_attr = want_attr ? io->out_attr : nullptr;
-        d_log = io->out_cell_log; d_status = io->out_status; d_steps = io->out_steps; d_fcell = io->out_cell;
-        d_edge = io->out_min_edge;
-        d_cell0_ext = io->cell0;
-    }
-    // (the kernel writes every output slot itself, zeros included -- see k_advect)
-    if (d_log) CK(cudaMemsetAsync(d_log, 0xff, (size_t)n * times * 4, st));
-
     if ((rc = ensure(ctx, ctx->p_cell_int, (size_t)n * 4))) return rc;
-    CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
-    P.pos = d_xyz; P.depth = d_depth;
-    P.out_pos = d_out_pos; P.out_vel = d_out_vel; P.out_attr = d_out_attr;
-    P.cell_log = d_log; P.status = d_status; P.steps = d_steps; P.fcell = d_fcell;
-    P.min_edge = d_edge;
-    P.diag_edge = (cfg->count_near_edge || d_edge) ? 1 : 0;
-    if ((rc = run_range(ctx, cfg, path, n, d_cell0_ext, (int*)ctx->p_cell_int.p, ctx->s_vals, ctx->s_vals2, ctx->s_keys2, ctx->s_tmp, P,
-                        ctx->ev2, ctx->ev3, ctx->ev1, nullptr)))
+
+    if (!host) {
+        // DEVICE memory: everything on the context's stream, asynchronous unless the caller asks for stats
+        CK(cudaEventRecord(ctx->ev0, st));
+        if (io->out_cell_log) CK(cudaMemsetAsync(io->out_cell_log, 0xff, (size_t)n * times * 4, st));
+        CK(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), st));
+        P.counters = ctx->counters;
+        P.pos = io->xyz; P.depth = io->depth;
+        P.out_pos = io->out_pos; P.out_vel = io->out_vel; P.out_attr = want_attr ? io->out_attr : nullptr;
+        P.cell_log = io->out_cell_log; P.status = io->out_status; P.steps = io->out_steps; P.fcell = io->out_cell;
+        P.min_edge = io->out_min_edge;
+        P.diag_edge = (cfg->count_near_edge || io->out_min_edge) ? 1 : 0;
+        if ((rc = run_range(ctx, cfg, path, n, io->cell0, (int*)ctx->p_cell_int.p, ctx->s_vals, ctx->s_vals2, ctx->s_keys2, ctx->s_tmp, P,
+                            ctx->ev2, ctx->ev3, ctx->ev1, ctx->ev_kend)))
+            return rc;
+        if ((rc = mark_use(ctx, front))) return rc;
+        if (path && back != front && (rc = mark_use(ctx, back))) return rc;
+        if (stats) {
+            unsigned long long h_counters[4] = {0, 0, 0, 0};
+            CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ctx->ev_end, st));
+            CK(cudaStreamSynchronize(st));
+            std::memset(stats, 0, sizeof(*stats));
+            stats->particle_steps = (int64_t)h_counters[0];
+            stats->alive_at_end = (int64_t)h_counters[1];
+            stats->near_edge_particles = (int64_t)h_counters[3];
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev_kend) == cudaSuccess) stats->kernel_ms = ms;
+            if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) stats->locate_ms = ms;
+            if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_end) == cudaSuccess) stats->total_ms = ms;
+            stats->launches = (int32_t)(ctx->launches - launches0);
+        }
+        return MOPS_OK;
+    }
+
+    // HOST memory: inputs go up on the copy_in stream into one of two staging sets, the kernels run on the main stream,
+    // end points first and then the recorded trajectories come back on the copy_out stream.  A second call submitted
+    // before the first is waited for uses the other set: its H2D and the first call's D2H overlap the kernels.
+    const long long tk = ++ctx->host_seq;
+    mops_ctx::HostSet& S = ctx->hset[tk & 1];
+    if (S.busy) { // the set's previous call (ticket tk - 2) was never waited for: finish it before its staging is reused
+        CK(cudaEventSynchronize(S.out_done));
+        S.busy = false;
+    }
+    if ((rc = ensure(ctx, S.xyz, (size_t)n * 24))) return rc;
+    if ((rc = ensure(ctx, S.depth, (size_t)n * 4))) return rc;
+    if ((rc = ensure(ctx, S.out_pos, out_bytes))) return rc;
+    if ((rc = ensure(ctx, S.out_vel, out_bytes))) return rc;
+    if (io->cell0 && (rc = ensure(ctx, S.cell0, (size_t)n * 4))) return rc;
+    if (want_attr && (rc = ensure(ctx, S.out_attr, out_bytes))) return rc;
+    if (io->out_cell_log && (rc = ensure(ctx, S.log, (size_t)n * times * 4))) return rc;
+    if (io->out_status && (rc = ensure(ctx, S.status, (size_t)n * 4))) return rc;
+    if (io->out_steps && (rc = ensure(ctx, S.steps, (size_t)n * 4))) return rc;
+    if (io->out_cell && (rc = ensure(ctx, S.fcell, (size_t)n * 4))) return rc;
+    if (io->out_min_edge && (rc = ensure(ctx, S.edge, (size_t)n * 8))) return rc;
+
+    cudaStream_t si = ctx->copy_in, so = ctx->copy_out;
+    CK(cudaEventRecord(S.begin, si));
+    CK(cudaMemcpyAsync(S.xyz.p, io->xyz, (size_t)n * 24, cudaMemcpyHostToDevice, si));
+    CK(cudaMemcpyAsync(S.depth.p, io->depth, (size_t)n * 4, cudaMemcpyHostToDevice, si));
+    if (io->cell0) CK(cudaMemcpyAsync(S.cell0.p, io->cell0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
+    CK(cudaEventRecord(S.in_done, si));
+
+    CK(cudaStreamWaitEvent(st, S.in_done, 0));
+    if (io->out_cell_log) CK(cudaMemsetAsync(S.log.p, 0xff, (size_t)n * times * 4, st));
+    CK(cudaMemsetAsync(S.d_counters, 0, 4 * sizeof(unsigned long long), st));
+    P.counters = S.d_counters;
+    P.pos = (double*)S.xyz.p; P.depth = (float*)S.depth.p;
+    P.out_pos = (double*)S.out_pos.p; P.out_vel = (double*)S.out_vel.p; P.out_attr = want_attr ? (double*)S.out_attr.p : nullptr;
+    P.cell_log = io->out_cell_log ? (int*)S.log.p : nullptr;
+    P.status = io->out_status ? (int*)S.status.p : nullptr;
+    P.steps = io->out_steps ? (int*)S.steps.p : nullptr;
+    P.fcell = io->out_cell ? (int*)S.fcell.p : nullptr;
+    P.min_edge = io->out_min_edge ? (double*)S.edge.p : nullptr;
+    P.diag_edge = (cfg->count_near_edge || P.min_edge) ? 1 : 0;
+    if ((rc = run_range(ctx, cfg, path, n, io->cell0 ? (const int*)S.cell0.p : nullptr, (int*)ctx->p_cell_int.p, ctx->s_vals, ctx->s_vals2,
+                        ctx->s_keys2, ctx->s_tmp, P, S.loc0, S.loc1, S.k0, S.k1)))
         return rc;
-    CK(cudaEventRecord(ctx->ev_kend, st));
     if ((rc = mark_use(ctx, front))) return rc;
     if (path && back != front && (rc = mark_use(ctx, back))) return rc;
 
-    unsigned long long h_counters[4] = {0, 0, 0, 0};
-    if (host) {
-        CK(cudaMemcpyAsync(io->xyz, d_xyz, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(io->depth, d_depth, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (!zero_copy_out) {
-            CK(cudaMemcpyAsync(io->out_pos, d_out_pos, out_bytes, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(io->out_vel, d_out_vel, out_bytes, cudaMemcpyDeviceToHost, st));
-            if (d_out_attr) CK(cudaMemcpyAsync(io->out_attr, d_out_attr, out_bytes, cudaMemcpyDeviceToHost, st));
-        }
-        if (d_log) CK(cudaMemcpyAsync(io->out_cell_log, d_log, (size_t)n * times * 4, cudaMemcpyDeviceToHost, st));
-        if (d_status) CK(cudaMemcpyAsync(io->out_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (d_steps) CK(cudaMemcpyAsync(io->out_steps, d_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (d_fcell) CK(cudaMemcpyAsync(io->out_cell, d_fcell, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (d_edge) CK(cudaMemcpyAsync(io->out_min_edge, d_edge, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamWaitEvent(so, S.k1, 0));
+    CK(cudaMemcpyAsync(io->xyz, S.xyz.p, (size_t)n * 24, cudaMemcpyDeviceToHost, so));
+    CK(cudaMemcpyAsync(io->depth, S.depth.p, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+    CK(cudaEventRecord(S.ends_done, so));
+    CK(cudaMemcpyAsync(io->out_pos, S.out_pos.p, out_bytes, cudaMemcpyDeviceToHost, so));
+    CK(cudaMemcpyAsync(io->out_vel, S.out_vel.p, out_bytes, cudaMemcpyDeviceToHost, so));
+    if (want_attr) CK(cudaMemcpyAsync(io->out_attr, S.out_attr.p, out_bytes, cudaMemcpyDeviceToHost, so));
+    if (io->out_cell_log) CK(cudaMemcpyAsync(io->out_cell_log, S.log.p, (size_t)n * times * 4, cudaMemcpyDeviceToHost, so));
+    if (io->out_status) CK(cudaMemcpyAsync(io->out_status, S.status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+    if (io->out_steps) CK(cudaMemcpyAsync(io->out_steps, S.steps.p, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+    if (io->out_cell) CK(cudaMemcpyAsync(io->out_cell, S.fcell.p, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+    if (io->out_min_edge) CK(cudaMemcpyAsync(io->out_min_edge, S.edge.p, (size_t)n * 8, cudaMemcpyDeviceToHost, so));
+    CK(cudaMemcpyAsync(S.h_counters, S.d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, so));
+    CK(cudaEventRecord(S.out_done, so));
+    S.busy = true;
+    S.ticket = tk;
+    S.launches = ctx->launches - launches0;
+    if (ticket) {
+        *ticket = tk;
+        return MOPS_OK;
     }
-    // host-memory calls complete before returning; device-memory calls stay asynchronous on the
-    // context's stream unless the caller asks for stats
-    if (host || stats) {
-        CK(cudaMemcpyAsync(h_counters, ctx->counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(ctx->ev_end, st));
-        CK(cudaStreamSynchronize(st));
-    }
-    if (stats) {
-        std::memset(stats, 0, sizeof(*stats));
-        stats->particle_steps = (int64_t)h_counters[0];
-        stats->alive_at_end = (int64_t)h_counters[1];
-        stats->near_edge_particles = (int64_t)h_counters[3];
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev_kend) == cudaSuccess) stats->kernel_ms = ms;
-        if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) stats->locate_ms = ms;
-        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_end) == cudaSuccess) stats->total_ms = ms;
-        stats->launches = (int32_t)(ctx->launches - launches0);
-    }
-    return MOPS_OK;
+    return host_wait(ctx, tk, 1, stats); // the plain HOST-mode call completes before it returns
 }
 
 template <int M>
@@ -933,15 +891,20 @@ int mops_create(mops_ctx** out, int device_ordinal)
               cudaEventCreate(&ctx->ev_kend) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess &&
               cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_nsel, sizeof(int)) == cudaSuccess;
+              cudaMalloc(&ctx->d_anyw, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_nsel, 2 * sizeof(int)) == cudaSuccess;
     if (const char* e = getenv("MOPS_SEGMENT_STEPS")) ctx->segment_steps = std::max(0, atoi(e));
     ctx->stream = ctx->own_stream;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 2; ++i)
-        ok = cudaEventCreateWithFlags(&ctx->pipe[i].in_done, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->pipe[i].k_done, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->pipe[i].out_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i) {
+        auto& S = ctx->hset[i];
+        ok = cudaEventCreate(&S.begin) == cudaSuccess && cudaEventCreateWithFlags(&S.in_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreate(&S.loc0) == cudaSuccess && cudaEventCreate(&S.loc1) == cudaSuccess && cudaEventCreate(&S.k0) == cudaSuccess &&
+             cudaEventCreate(&S.k1) == cudaSuccess && cudaEventCreateWithFlags(&S.ends_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreate(&S.out_done) == cudaSuccess && cudaMalloc(&S.d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+             cudaHostAlloc(&S.h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    }
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->marks[i]) == cudaSuccess;
     for (int i = 0; ok && i < MOPS_MAX_SNAPSHOT_SLOTS; ++i) {
         ok = cudaEventCreate(&ctx->snap[i].ready) == cudaSuccess && cudaEventCreate(&ctx->snap[i].last_use) == cudaSuccess;
@@ -966,23 +929,22 @@ void mops_destroy(mops_ctx* ctx)
         if (s.last_use) cudaEventDestroy(s.last_use);
     }
     Buf* bufs[] = {&ctx->st_zonal, &ctx->st_merid, &ctx->st_thick, &ctx->st_wtop, &ctx->st_bottom, &ctx->st_ztopc, &ctx->st_attr,
-                   &ctx->st_vmono, &ctx->p_xyz, &ctx->p_depth, &ctx->p_cell0, &ctx->p_cell_int, &ctx->p_out_pos, &ctx->p_out_vel,
-                   &ctx->p_out_attr, &ctx->p_log, &ctx->p_status, &ctx->p_steps, &ctx->p_fcell, &ctx->p_edge, &ctx->s_keys, &ctx->s_vals,
+                   &ctx->st_vmono, &ctx->p_xyz, &ctx->p_cell0, &ctx->p_cell_int, &ctx->s_keys, &ctx->s_vals,
                    &ctx->s_keys2, &ctx->s_vals2, &ctx->s_tmp, &ctx->s_state, &ctx->r_img0, &ctx->r_img1, &ctx->r_cells};
     for (Buf* b : bufs) cudaFree(b->p);
-    for (auto& ps : ctx->pipe) {
-        Buf* pb[] = {&ps.xyz, &ps.depth, &ps.cell0, &ps.cell_int, &ps.vals, &ps.vals2, &ps.keys2, &ps.tmp, &ps.out_pos, &ps.out_vel,
-                     &ps.out_attr, &ps.log, &ps.status, &ps.steps, &ps.fcell, &ps.edge};
+    for (auto& S : ctx->hset) {
+        Buf* pb[] = {&S.xyz, &S.depth, &S.cell0, &S.out_pos, &S.out_vel, &S.out_attr, &S.log, &S.status, &S.steps, &S.fcell, &S.edge};
         for (Buf* b : pb) cudaFree(b->p);
-        if (ps.in_done) cudaEventDestroy(ps.in_done);
-        if (ps.k_done) cudaEventDestroy(ps.k_done);
-        if (ps.out_done) cudaEventDestroy(ps.out_done);
+        cudaFree(S.d_counters);
+        if (S.h_counters) cudaFreeHost(S.h_counters);
+        cudaEvent_t evs[] = {S.begin, S.in_done, S.loc0, S.loc1, S.k0, S.k1, S.ends_done, S.out_done};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     }
-    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     cudaFree(ctx->counters);
     cudaFree(ctx->d_nonmono);
+    cudaFree(ctx->d_anyw);
     cudaFree(ctx->d_nsel);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
     cudaEventDestroy(ctx->ev_kend); cudaEventDestroy(ctx->ev_end);
@@ -1320,13 +1282,42 @@ int mops_locate(mops_ctx* ctx, int32_t mem, int64_t n, const double* xyz, int32_
 
 int mops_streamline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io, mops_traj_stats* stats)
 {
-    return trajectory_impl(ctx, cfg, slot, slot, io, stats, false);
+    return trajectory_impl(ctx, cfg, slot, slot, io, stats, false, nullptr);
 }
 
 int mops_pathline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot, const mops_traj_io* io,
                   mops_traj_stats* stats)
 {
-    return trajectory_impl(ctx, cfg, front_slot, back_slot, io, stats, true);
+    return trajectory_impl(ctx, cfg, front_slot, back_slot, io, stats, true, nullptr);
+}
+
+int mops_streamline_submit(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io, int64_t* ticket)
+{
+    if (!ticket) return MOPS_E_INVALID;
+    long long tk = 0;
+    const int rc = trajectory_impl(ctx, cfg, slot, slot, io, nullptr, false, &tk);
+    *ticket = tk;
+    return rc;
+}
+
+int mops_pathline_submit(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot, const mops_traj_io* io,
+                         int64_t* ticket)
+{
+    if (!ticket) return MOPS_E_INVALID;
+    long long tk = 0;
+    const int rc = trajectory_impl(ctx, cfg, front_slot, back_slot, io, nullptr, true, &tk);
+    *ticket = tk;
+    return rc;
+}
+
+int mops_traj_wait(mops_ctx* ctx, int64_t ticket, int32_t what, mops_traj_stats* stats)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (ticket == 0) { // n == 0 submit: nothing was enqueued
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        return MOPS_OK;
+    }
+    return host_wait(ctx, ticket, what, stats);
 }
 
 int mops_remap_fixed_depth(mops_ctx* ctx, const mops_remap_cfg* cfg, int32_t slot, double* img0, double* img1, int32_t* pixel_cell,

@@ -31,10 +31,6 @@ namespace mops {
 // row offset (vertex id * L) into the vertex-major snapshot arrays: unsigned, so address arithmetic needs no sign word
 typedef unsigned voff_t;
 
-#ifndef MOPS_UNROLL_SNAP
-#define MOPS_UNROLL_SNAP 0
-#endif
-
 // ---- resident mesh ----------------------------------------------------------------------
 template <int M>
 struct alignas(32) CellRec {
@@ -45,6 +41,7 @@ struct alignas(32) CellRec {
     double vx[M], vy[M], vz[M]; // vertex positions
     double nx[M], ny[M], nz[M]; // cross(v_k, v_(k+1)%nv)                      (TK:45)
     double B[M];                // triangle_area(v_(i-1), v_i, v_(i+1))       (Interpolation.hpp:154)
+    double ex[M], ey[M], ez[M]; // v_(k+1)%nv - v_k: the point-independent edge of triangle_area(v_k, v_k+1, p) (Interpolation.hpp:100)
 };
 
 struct VertRec {      // per Voronoi vertex, mesh-constant part of the cell->vertex interpolation
@@ -63,7 +60,8 @@ struct SnapView {
 
 enum {
     ST_ALIVE = 0, ST_BAD_CELL = 1, ST_NOT_IN_CELL = 2, ST_BAD_COLUMN = 3, ST_ZERO_VELOCITY = 4,
-    ST_ABOVE_SURFACE = 5, ST_BAD_SETUP = 6
+    ST_ABOVE_SURFACE = 5, ST_BAD_SETUP = 6,
+    ST_GENERIC = -1 // internal: the hexagon fast path does not cover this evaluation, take the generic one
 };
 
 // ---- Wachspress weights + in-cell test ------------------------------------------------
@@ -158,6 +156,58 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
     for (int i = 0; i < M; ++i)
         if (i < nv) w[i] *= recp;
     wfinite = isfinite(sum) && isfinite(recp) && (sum > 0.0);
+}
+
+// Hexagon fast path of CalcPolygonWachspress (nv == M): the same quotients with three point-independent pieces removed.
+//  * the edge v_(k+1) - v_k of triangle_area comes from the record (computed by the same subtraction at mesh set-up);
+//  * the '/ 2.0' of the six triangle areas is dropped: scaling by a power of two commutes with rounding, so with
+//    a_k = 2 A_k every quotient is fl(B_i / (a_(i-1) a_i)) = w_i / 4 exactly, the sum is sum / 4, its reciprocal 4 / sum and
+//    the normalised weights (w_i / 4) * (4 / sum) are bit-identical to the reference's -- as long as nothing under- or
+//    overflows, which the range windows below guarantee (a group outside them is not covered: ok = false);
+//  * roots, quotients and the reciprocal run as the branch-free exact sequences of dmath.cuh with ONE range decision at the
+//    end, so there is no slow-path merge inside the hot code.
+// ok = false: not covered (operands outside the windows, e.g. a point exactly on an edge) -> caller takes the generic path.
+template <int M>
+__device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, double px, double py, double pz, double (&w)[M], bool& ok)
+{
+    double a[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const double e1x = rec->ex[k], e1y = rec->ey[k], e1z = rec->ez[k];
+        const double e2x = px - rec->vx[k], e2y = py - rec->vy[k], e2z = pz - rec->vz[k];
+        const double cx = e1y * e2z - e1z * e2y;
+        const double cy = e1z * e2x - e1x * e2z;
+        const double cz = e1x * e2y - e1y * e2x;
+        a[k] = cx * cx + cy * cy + cz * cz;
+    }
+    unsigned mn = hi_raw(a[0]), mx = mn;
+#pragma unroll
+    for (int k = 1; k < M; ++k) {
+        mn = min(mn, hi_raw(a[k]));
+        mx = max(mx, hi_raw(a[k]));
+    }
+    ok = (mn >= 0x03500000u && mx < 0x7ff00000u); // nvcc's own fast-path range of sqrt
+#pragma unroll
+    for (int k = 0; k < M; ++k) a[k] = sq_fast(a[k]);
+    double den[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) den[i] = a[(i + M - 1) % M] * a[i]; // A_i of vertex i is area(v_(i-1), v_i, p)
+    unsigned wmn = 0xffffffffu, wmx = 0u;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        w[i] = div_by(rec->B[i], den[i], recip_refine(den[i]));
+        wmn = min(wmn, min(hi_raw(den[i]), hi_raw(w[i])));
+        wmx = max(wmx, max(hi_raw(den[i]), hi_raw(w[i])));
+    }
+    double sum = w[0]; // reference: sum = 0.0; sum += w[0] -> 0.0 + w[0] == w[0] for w[0] > 0
+#pragma unroll
+    for (int i = 1; i < M; ++i) sum += w[i];
+    const double recp = div_by(1.0, sum, recip_refine(sum));
+    wmn = min(wmn, min(hi_raw(sum), hi_raw(recp)));
+    wmx = max(wmx, max(hi_raw(sum), hi_raw(recp)));
+    ok = ok && (wmn >= WIN_LO && wmx < WIN_HI);
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] *= recp;
 }
 
 // returns false when the point is not in the cell (IsInMesh); else fills the normalised weights
@@ -437,7 +487,9 @@ __device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, co
 // levels `layer` (d*) and `layer - 1` (u*) of one snapshot in one pass over the vertices: one record pointer per
 // vertex, the upper level at a fixed -32 B offset.  Every accumulator sums in vertex order exactly as
 // gather_velw does, so the results are bit-equal to two gather_velw calls.
-template <int M, bool FULL = false>
+// NOW = true (hexagon fast path of a snapshot uploaded WITHOUT vertVelocityTop): the w component of every record is +0.0 and
+// the weights are finite and positive, so both vertical sums are exactly +0.0 and are not accumulated.
+template <int M, bool FULL = false, bool NOW = false>
 __device__ __forceinline__ void gather_velw_pair(const double4* __restrict__ velw, const voff_t (&vo)[M], const double (&w)[M], int nv,
                                                  int layer, double& dx, double& dy, double& dz, double& dw,
                                                  double& ux, double& uy, double& uz, double& uw)
@@ -453,11 +505,11 @@ __device__ __forceinline__ void gather_velw_pair(const double4* __restrict__ vel
             dx += w[i] * d.x;
             dy += w[i] * d.y;
             dz += w[i] * d.z;
-            dw += w[i] * d.w;
+            if (!NOW) dw += w[i] * d.w;
             ux += w[i] * u.x;
             uy += w[i] * u.y;
             uz += w[i] * u.z;
-            uw += w[i] * u.w;
+            if (!NOW) uw += w[i] * u.w;
         }
     }
 }
@@ -497,7 +549,10 @@ struct EvalOut {
 };
 
 // calc_velocity_at (streamline), VK:740-872.  Returns ST_ALIVE or the reason of failure.
-template <int M, bool FULL = false>
+// FULL = true is the hexagon fast path (nv == M): it covers cells whose columns are monotone and points whose weight
+// arithmetic stays inside the exact-sequence windows, and returns ST_GENERIC for everything else (the caller then runs the
+// generic evaluation, FULL = false, which is the complete restatement).  NOW: see gather_velw_pair.
+template <int M, bool FULL = false, bool NOW = false>
 __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, const SnapView& s, bool mono, int L,
                                            const d3& p, double depth, int& hint, EvalOut& o)
 {
@@ -505,13 +560,20 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
     if (nv <= 0) return ST_BAD_SETUP;
     double w[M];
     bool wfinite = false;
-    if (!cell_weights<M, FULL>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    if (FULL) {
+        if (!mono) return ST_GENERIC;
+        if (!in_mesh<M, true>(rec, nv, p.x, p.y, p.z)) return ST_NOT_IN_CELL;
+        hex_weights<M>(rec, p.x, p.y, p.z, w, wfinite);
+        if (!wfinite) return ST_GENERIC;
+    } else {
+        if (!cell_weights<M, false>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    }
     voff_t vo[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? (voff_t)rec->vid[i] * (voff_t)L : 0u;
 
     LayerRes lr;
-    if (mono && wfinite) lr = layer_search_stream<M, FULL>(ZCol<M, FULL>{s.ztop, w, vo, nv, L}, depth, hint);
+    if (FULL || (mono && wfinite)) lr = layer_search_stream<M, FULL>(ZCol<M, FULL>{s.ztop, w, vo, nv, L}, depth, hint);
     else lr = slow_layer_stream<M>(rec, s.ztop, L, p.x, p.y, p.z, depth);
     const int layer = lr.layer;
     const double ztop_up = lr.top, ztop_dn = lr.bot;
@@ -524,14 +586,14 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
     const double t = (x - ztop_dn) / denom;
 
     double dx, dy, dz, dw, ux, uy, uz, uw;
-    gather_velw_pair<M, FULL>(s.velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
+    gather_velw_pair<M, FULL, FULL && NOW>(s.velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
     if (tiny_len(dx, dy, dz) || tiny_len(ux, uy, uz)) return ST_ZERO_VELOCITY; // VK:845-847
     const double omt = 1.0 - t;
     o.hx = t * ux + omt * dx; // VK:849
     o.hy = t * uy + omt * dy;
     o.hz = t * uz + omt * dz;
     if (tiny_len(o.hx, o.hy, o.hz)) return ST_ZERO_VELOCITY;
-    o.vv = t * uw + omt * dw; // VK:870 (levels `layer`, `layer-1` of vertVelocityTop)
+    o.vv = (FULL && NOW) ? 0.0 : t * uw + omt * dw; // VK:870 (levels `layer`, `layer-1` of vertVelocityTop)
     o.a0 = 0.0; o.a1 = 0.0;
     return ST_ALIVE;
 }
@@ -539,8 +601,8 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
 // calc_velocity_at (pathline), VK:1124-1327: front and back interpolated separately (own layer
 // search each, shared weights), blended with alpha; no zero-velocity reject.  sv[0] = front,
 // sv[1] = back; the two snapshots go through ONE copy of the code (loops kept rolled) to
-// keep the kernel's instruction footprint down.
-template <int M, bool FULL = false>
+// keep the kernel's instruction footprint down.  FULL / NOW as in eval_stream.
+template <int M, bool FULL = false, bool NOW = false>
 __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv,
                                          bool mono_f, bool mono_b, int L, int attr_count, const d3& p, double depth,
                                          double alpha, int& hint_f, int& hint_b, EvalOut& o)
@@ -549,7 +611,14 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
     if (nv <= 0) return ST_BAD_SETUP;
     double w[M];
     bool wfinite = false;
-    if (!cell_weights<M, FULL>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    if (FULL) {
+        if (!(mono_f && mono_b)) return ST_GENERIC;
+        if (!in_mesh<M, true>(rec, nv, p.x, p.y, p.z)) return ST_NOT_IN_CELL;
+        hex_weights<M>(rec, p.x, p.y, p.z, w, wfinite);
+        if (!wfinite) return ST_GENERIC;
+    } else {
+        if (!cell_weights<M, false>(rec, nv, p.x, p.y, p.z, w, wfinite)) return ST_NOT_IN_CELL;
+    }
     voff_t vo[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) vo[i] = (FULL || i < nv) ? (voff_t)rec->vid[i] * (voff_t)L : 0u;
@@ -557,14 +626,12 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
     // both layer searches first (VK:1182-1222) ...
     int lf = -1, lb = -1;
     double f_up = 0.0, f_dn = 0.0, b_up = 0.0, b_dn = 0.0;
-    // front/back through one rolled copy of the code by default; MOPS_UNROLL_SNAP=1 unrolls the hexagon fast path
-    constexpr int US = (FULL && MOPS_UNROLL_SNAP) ? 2 : 1;
-#pragma unroll US
+#pragma unroll 1
     for (int s = 0; s < 2; ++s) {
         const bool mono = s ? mono_b : mono_f;
         const int hint = s ? hint_b : hint_f;
         LayerRes r;
-        if (mono && wfinite) r = layer_search_path<M, FULL>(ZCol<M, FULL>{sv[s].ztop, w, vo, nv, L}, depth, hint);
+        if (FULL || (mono && wfinite)) r = layer_search_path<M, FULL>(ZCol<M, FULL>{sv[s].ztop, w, vo, nv, L}, depth, hint);
         else r = slow_layer_path<M>(rec, sv[s].ztop, L, p.x, p.y, p.z, depth);
         if (s == 0) { lf = r.layer; f_up = r.top; f_dn = r.bot; }
         else { lb = r.layer; b_up = r.top; b_dn = r.bot; }
@@ -592,15 +659,15 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
     // ... then the gathers and the alpha blend (VK:1243-1324)
     const double oma = 1.0 - alpha;
     double ffx = 0.0, ffy = 0.0, ffz = 0.0, ffw = 0.0, fa0 = 0.0, fa1 = 0.0;
-#pragma unroll US
+#pragma unroll 1
     for (int s = 0; s < 2; ++s) {
         const int layer = s ? lb : lf;
         const double t = s ? t_back : t_front;
         const double omt = 1.0 - t;
         double dx, dy, dz, dw, ux, uy, uz, uw;
-        gather_velw_pair<M, FULL>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
+        gather_velw_pair<M, FULL, FULL && NOW>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
         const double vx = t * ux + omt * dx, vy = t * uy + omt * dy, vz = t * uz + omt * dz;
-        const double vw = t * uw + omt * dw;
+        const double vw = (FULL && NOW) ? 0.0 : t * uw + omt * dw;
         double a0 = 0.0, a1 = 0.0;
         if (attr_count >= 1) {
             const double ad = gather_scalar<M, FULL>(sv[s].attr0, vo, w, nv, layer), au = gather_scalar<M, FULL>(sv[s].attr0, vo, w, nv, layer - 1);
@@ -616,7 +683,7 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
             o.hx = alpha * vx + oma * ffx; // VK:1259
             o.hy = alpha * vy + oma * ffy;
             o.hz = alpha * vz + oma * ffz;
-            o.vv = alpha * vw + oma * ffw; // VK:1286
+            o.vv = (FULL && NOW) ? 0.0 : alpha * vw + oma * ffw; // VK:1286
             o.a0 = (attr_count >= 1) ? alpha * a0 + oma * fa0 : 0.0;
             o.a1 = (attr_count >= 2) ? alpha * a1 + oma * fa1 : 0.0;
         }

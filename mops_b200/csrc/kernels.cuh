@@ -3,6 +3,7 @@
 // ST = src/CPU/TBB/MPASOSolutionTBB.cpp of the reference.
 #pragma once
 #include "engine.cuh"
+#include "fastpath.cuh"
 
 namespace mops {
 
@@ -28,8 +29,12 @@ __global__ void k_build_records(CellRec<M>* __restrict__ rec, int nC)
             r->ny[k] = az * bx - ax * bz;
             r->nz[k] = ax * by - ay * bx;
             r->B[k] = tri_area(r->vx[kp], r->vy[kp], r->vz[kp], ax, ay, az, bx, by, bz);
+            r->ex[k] = bx - ax; // e1 of triangle_area(v_k, v_k+1, p), Interpolation.hpp:100
+            r->ey[k] = by - ay;
+            r->ez[k] = bz - az;
         } else {
             r->nx[k] = 0.0; r->ny[k] = 0.0; r->nz[k] = 0.0; r->B[k] = 0.0;
+            r->ex[k] = 0.0; r->ey[k] = 0.0; r->ez[k] = 0.0;
         }
     }
 }
@@ -201,7 +206,7 @@ __global__ void k_cell_ztop(const double* __restrict__ thick, const double* __re
 __global__ void k_vertex_fields(const VertRec* __restrict__ vert, const int* __restrict__ vcell_ext, const double4* __restrict__ trig,
                                 const double* __restrict__ ztop_c, const double* __restrict__ zonal, const double* __restrict__ merid,
                                 const double* __restrict__ wtop, double* __restrict__ ztop_v, double4* __restrict__ velw_v,
-                                int nV, int L)
+                                int nV, int L, int* __restrict__ any_w)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)nV * L) return;
@@ -236,6 +241,8 @@ __global__ void k_vertex_fields(const VertRec* __restrict__ vert, const int* __r
     }
     ztop_v[idx] = zt;
     velw_v[idx] = o;
+    // does the snapshot carry any vertical velocity?  (bit test: -0.0 and NaN count as "yes"; see gather_velw_pair NOW)
+    if (__double_as_longlong(o.w) != 0ll) *any_w = 1;
 }
 
 // CalcCellCenterToVertex (ST:57-106): scalar attribute, clamped >= 0
@@ -321,6 +328,7 @@ struct AdvectParams {
     int nC, L;
     SnapView sv[2];   // [0] front, [1] back (pathline)
     int attr_count;   // pathline attributes in use (0..2)
+    int no_w;         // host-side dispatch only: neither snapshot carries vertVelocityTop (NOW instantiations)
     int use_euler;
     int delta_t;      // signed seconds
     int times;        // steps
@@ -349,6 +357,7 @@ struct AdvectParams {
     // to the live ones before the next segment, so lanes of stopped particles do not ride along to the end.
     int step_begin, step_end;
     struct AdvState* state; // [n], indexed by particle
+    const int* n_live;      // device-side particle count of this launch (the previous compaction's output) or null: P.n
 };
 
 struct alignas(32) AdvState {
@@ -358,9 +367,17 @@ struct alignas(32) AdvState {
     int pad;
 };
 
-struct AdvAliveOp { // cub::DeviceSelect::If predicate over particle indices
+// cub::DeviceSelect::Flagged flag of position i of the processing order: inside the live prefix (whose length is on the
+// device, so the host never reads it back and a segmented call stays asynchronous) and still alive
+struct AdvAliveFlag {
+    const int* order;
     const AdvState* state;
-    __device__ __forceinline__ bool operator()(const int pid) const { return state[pid].alive != 0; }
+    const int* n_live; // null: every position is live (first compaction)
+    __device__ __forceinline__ bool operator()(const int i) const
+    {
+        if (n_live && i >= *n_live) return false;
+        return state[order[i]].alive != 0;
+    }
 };
 
 __device__ __forceinline__ void st3(double* p, long long i, double x, double y, double z)
@@ -370,9 +387,6 @@ __device__ __forceinline__ void st3(double* p, long long i, double x, double y, 
 
 __device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : ((1.0 < v) ? 1.0 : v); }
 
-#ifndef MOPS_COLD_GENERIC
-#define MOPS_COLD_GENERIC 0 // 1 = the generic (nv != record width) evaluation of 6-wide meshes is a call; not yet measured on B200
-#endif
 struct EvalPacked {
     EvalOut o;
     int st, hint_f, hint_b;
@@ -391,11 +405,6 @@ __device__ __noinline__ EvalPacked eval_generic_cold(const CellRec<M>* __restric
     return r;
 }
 
-// EXTRA = false is the production instantiation; EXTRA = true additionally honours P.walk
-// (MOPS_SEM_WALK) and P.diag_edge (near-edge counting) -- kept out of the hot variant because even
-// never-taken branches cost registers and ~4 % of the kernel time here.
-// ATTR = true carries the pathline's scalar attributes (P.attr_count > 0 and an output buffer); without it the
-// attribute accumulators do not exist.
 // Block size / resident blocks of the advection kernel: build-time knobs so occupancy variants can be A/B'd
 // (scripts/gpu_ab.sh); the defaults are the measured best on B200.
 #ifndef MOPS_ADV_BLOCK
@@ -404,25 +413,178 @@ __device__ __noinline__ EvalPacked eval_generic_cold(const CellRec<M>* __restric
 #ifndef MOPS_ADV_MINB
 #define MOPS_ADV_MINB 3
 #endif
-#ifndef MOPS_ROLL_RELOC
-#define MOPS_ROLL_RELOC 0 // 1 = rolled cell relocation (smaller hot code); not yet measured on B200
-#endif
-// SEG = true: the launch covers steps [P.step_begin, P.step_end) only (see AdvectParams::state); SEG = false is the
-// single-launch kernel (every SEG-only branch folds away at compile time).
-template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR, bool SEG = false>
-__global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectParams P)
+
+// state of one particle that a step reads and writes (by value in and out of the generic step, so that the caller's
+// copies stay in registers when the generic step is an out-of-line call)
+struct StepIO {
+    d3 pos;           // in: start of step, out: end of step
+    d3 hvel;          // out: the step's velocity (RK4: weighted mean of the four stages)
+    double at0, at1;  // out: pathline attributes of the step
+    double edge_min;  // in/out: smallest edge distance seen (EXTRA diagnostic)
+    float depth_f;    // in/out
+    int hint_f, hint_b;
+    int status;       // out: ST_ALIVE or why the particle stopped (then nothing else is valid)
+};
+
+// One step of StreamLine / PathLine after the cell relocation, exactly as the reference does it (VK:923-986 / VK:1391-1465):
+// Euler = one stage, RK4 = four, all stages against the start-of-step cell (R1); position, depth and radius update.
+// This is the complete restatement: every instantiation without the straight-line fast path runs it inline, the
+// production hexagon kernels call it out of line for the steps the fast path does not cover.
+template <int M, bool PATH, bool EXTRA, bool ATTR>
+__device__ __forceinline__ StepIO step_generic(const AdvectParams& P, int cell, int step, StepIO io)
 {
+    const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
+    const CellRec<M>* __restrict__ rec = recs + cell;
+    const d3 pos = io.pos;
+    const double dt = (double)P.delta_t;
+    const double dalpha = PATH ? dt / P.duration : 0.0; // VK:1401
+    const bool mono_f = P.sv[0].mono[cell] != 0;
+    const bool mono_b = PATH ? (P.sv[1].mono[cell] != 0) : false;
+    const double cur_depth = -1.0 * (double)io.depth_f;
+    const double alpha = PATH ? (double)step / (double)P.times : 0.0; // VK:1345
+    const double r = len3(pos);
+    int hint_f = io.hint_f, hint_b = io.hint_b;
+    d3 hvel = mk3(0.0, 0.0, 0.0);
+    double vvel = 0.0, at0 = 0.0, at1 = 0.0;
+    d3 new_pos;
+    EvalOut o;
+
+    // One rolled loop => one inlined copy of the evaluation.
+    const int n_stage = P.use_euler ? 1 : 4;
+    d3 hprev = mk3(0.0, 0.0, 0.0);
+    int st = ST_ALIVE;
+#pragma unroll 1
+    for (int s = 0; s < n_stage; ++s) {
+        d3 p = pos;
+        double a_s = alpha;
+        if (s > 0) {
+            p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5, r);
+            if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
+        }
+        const CellRec<M>* __restrict__ rec_s = rec;
+        bool mf = mono_f, mb = mono_b;
+        if (EXTRA && P.walk && s > 0) { // MOPS_SEM_WALK: the cell that contains this stage point
+            const int cs = walk_nearest<M>(recs, P.c4, cell, p.x, p.y, p.z);
+            rec_s = recs + cs;
+            mf = P.sv[0].mono[cs] != 0;
+            mb = PATH ? (P.sv[1].mono[cs] != 0) : false;
+        }
+        if (EXTRA && P.diag_edge) {
+            const double a = min_edge_angle<M>(rec_s, rec_s->nv, p.x, p.y, p.z);
+            if (a < io.edge_min) io.edge_min = a;
+        }
+        if (M == 6) {
+            // hexagon form of the evaluation (nv == M: no per-slot selects); whatever it does not cover (ST_GENERIC: the
+            // 12 pentagons, coast cells, non-monotone columns, weight arithmetic outside the exact-sequence windows) takes
+            // the general form out of line
+            st = ST_GENERIC;
+            if (rec_s->nv == M)
+                st = PATH ? eval_path<M, true>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
+                          : eval_stream<M, true>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
+            if (st == ST_GENERIC) {
+                const EvalPacked g = eval_generic_cold<M, PATH>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p.x, p.y, p.z,
+                                                                cur_depth, a_s, hint_f, hint_b);
+                st = g.st; hint_f = g.hint_f; hint_b = g.hint_b; o = g.o;
+            }
+        } else {
+            st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
+                      : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
+        }
+        if (st != ST_ALIVE) break;
+        if (s == 0) {
+            hvel = mk3(o.hx, o.hy, o.hz);
+            vvel = o.vv;
+            if (ATTR) { at0 = o.a0; at1 = o.a1; }
+        } else {
+            const double c = (s == 3) ? 1.0 : 2.0; // s1 + 2 s2 + 2 s3 + s4, left to right (VK:959-960)
+            hvel.x = hvel.x + c * o.hx;
+            hvel.y = hvel.y + c * o.hy;
+            hvel.z = hvel.z + c * o.hz;
+            vvel = vvel + c * o.vv;
+            if (ATTR) {
+                at0 = at0 + c * o.a0;
+                at1 = at1 + c * o.a1;
+            }
+        }
+        hprev = mk3(o.hx, o.hy, o.hz);
+    }
+    io.status = st;
+    io.hint_f = hint_f; io.hint_b = hint_b;
+    if (st != ST_ALIVE) return io;
+    if (P.use_euler) {
+        new_pos = rotate_euler(pos, hvel, P.delta_t, r); // VK:968-972
+    } else {
+        { // (s1 + 2 s2 + 2 s3 + s4) / 6.0: six quotients by one constant
+            const double a6[6] = {hvel.x, hvel.y, hvel.z, vvel, at0, at1};
+            double q6[6];
+            bool ok6 = true;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) q6[i] = div_by6(a6[i], ok6);
+            if (!ok6) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) q6[i] = slow_div(a6[i], 6.0);
+            }
+            hvel.x = q6[0]; hvel.y = q6[1]; hvel.z = q6[2];
+            vvel = q6[3];
+            at0 = q6[4]; at1 = q6[5];
+        }
+        const double tx = pos.x + hvel.x * dt, ty = pos.y + hvel.y * dt, tz = pos.z + hvel.z * dt; // VK:962-964
+        const double tl = len3(tx, ty, tz);
+        if (tl > 1e-12) {
+            double ux, uy, uz;
+            div3(tx, ty, tz, tl, ux, uy, uz);
+            new_pos = mk3(ux * r, uy * r, uz * r);
+        } else {
+            new_pos = pos;
+        }
+    }
+    // depth / radius update with the float round trip (VK:977-986, R3, R4)
+    const double old_depth = (double)io.depth_f;
+    double new_depth = old_depth - vvel * (double)P.delta_t;
+    new_depth = (0.0 < new_depth) ? new_depth : 0.0;
+    const double r_sum = r + vvel * (double)P.delta_t;
+    const double r_new = (1.0 < r_sum) ? r_sum : 1.0;
+    io.depth_f = (float)new_depth;
+    const double nlen = len3(new_pos);
+    if (nlen > 1e-12) {
+        double ux, uy, uz;
+        div3(new_pos.x, new_pos.y, new_pos.z, nlen, ux, uy, uz);
+        new_pos = mk3(ux * r_new, uy * r_new, uz * r_new);
+    }
+    io.pos = new_pos;
+    io.hvel = hvel;
+    io.at0 = at0; io.at1 = at1;
+    return io;
+}
+
+template <int M, bool PATH, bool EXTRA, bool ATTR>
+__device__ __noinline__ StepIO step_generic_cold(const AdvectParams& P, int cell, int step, StepIO io)
+{
+    return step_generic<M, PATH, EXTRA, ATTR>(P, cell, step, io);
+}
+
+// EXTRA = false is the production instantiation; EXTRA = true additionally honours P.walk (MOPS_SEM_WALK) and P.diag_edge
+// (near-edge counting) -- kept out of the hot variant because even never-taken branches cost registers and time.
+// ATTR = true carries the pathline's scalar attributes (P.attr_count > 0 and an output buffer).
+// SEG = true: the launch covers steps [P.step_begin, P.step_end) only (see AdvectParams::state); SEG = false is a
+// single-launch kernel (every SEG-only branch folds away at compile time).
+// NOW = true: neither snapshot of the call carries vertVelocityTop, see gather_velw_pair / fastpath.cuh.
+// FAST = true (hexagonal meshes, no attributes, no diagnostics): RK4 steps on hexagons with monotone columns run the
+// straight-line form of fastpath.cuh; step_generic is called out of line for every step it does not cover.
+template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR, bool SEG = false, bool NOW = false, bool FAST = false>
+__global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const __grid_constant__ AdvectParams P)
+{
+    static_assert(!FAST || (M == 6 && !EXTRA && !ATTR), "the straight-line path is the hexagon / no-attribute / no-diagnostic form");
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0, my_alive = 0, my_near = 0;
-    if (tix < P.n) {
+    const long long n_act = (SEG && P.n_live) ? (long long)*P.n_live : P.n;
+    if (tix < n_act) {
         const long long pid = P.order ? (long long)P.order[tix] : tix;
         const CellRec<M>* __restrict__ recs = reinterpret_cast<const CellRec<M>*>(P.rec);
         d3 pos = mk3(P.pos[3 * pid], P.pos[3 * pid + 1], P.pos[3 * pid + 2]);
         float depth_f = P.depth[pid];
         int cell = P.cell0[pid];
         const long long base = pid * (long long)P.each;
-        const double dt = (double)P.delta_t;
-        const double dalpha = PATH ? dt / P.duration : 0.0; // VK:1401
         int status = ST_ALIVE;
         int started = 0;
         int run_time = 0;
@@ -440,11 +602,13 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
             run_time = step_lo * abs(P.delta_t);
         }
         const int started0 = started;
+        // FAST: alpha = step / times and dalpha as exact quotients without nvcc's per-division branch
+        const double x_times = FAST ? recip_refine((double)P.times) : 0.0;
+        const double dalpha_f = (FAST && PATH) ? (double)P.delta_t / P.duration : 0.0; // VK:1401
 
         // Every output slot is written exactly once by this thread (no host-side memset of the buffers,
         // which may be pinned host memory written over PCIe): the reference's buffers are
         // value-initialised (TrajectoryCommon.h:20-25), so slots it never reaches hold (0,0,0).
-        const bool has_attr_out = PATH && P.attr_count > 0 && P.out_attr;
         if (cell < 0 || cell >= P.nC) {
             status = ST_BAD_CELL; // VK:895-897: nothing is written, not even the seed
         } else {
@@ -458,51 +622,7 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                 if (step > 0) {
                     // relocation: argmin over {cellsOnCell[c][0..nv-1], c} of |centre - x|, strict <,
                     // that order, one ring (VK:903-921; GetCellNeighborsIdx TK:74-101)
-#if MOPS_ROLL_RELOC
-                    // rolled form (one candidate at a time, three short loops): same candidates, same order, same
-                    // compares as the unrolled form below, in ~1/5 of its instruction footprint -- relocation runs once
-                    // per step, the evaluation four times, and the kernel's hot code sits at the L1.5 I-cache size
                     const CellRec<M>* r = recs + cell;
-                    int best = cell;
-                    double m1 = 1.7976931348623157e308;
-#pragma unroll 1
-                    for (int k = 0; k <= M; ++k) {
-                        const int c = (k < M) ? r->nbr[k] : cell;
-                        if (c >= 0) {
-                            const double4 cc = ldg_d4(P.c4 + c);
-                            const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
-                            const double l = dx * dx + dy * dy + dz * dz;
-                            if (l < m1) { m1 = l; best = c; }
-                        }
-                    }
-                    const double lim = m1 + m1 * 0x1p-48;
-                    int close = 0;
-#pragma unroll 1
-                    for (int k = 0; k <= M; ++k) {
-                        const int c = (k < M) ? r->nbr[k] : cell;
-                        if (c >= 0) {
-                            const double4 cc = ldg_d4(P.c4 + c);
-                            const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
-                            close += (dx * dx + dy * dy + dz * dz <= lim) ? 1 : 0;
-                        }
-                    }
-                    if (close > 1 || !(m1 < 1.0e300)) { // near-tie: compare the roots as the reference does
-                        double min_len = 1.7976931348623157e308;
-                        best = cell;
-#pragma unroll 1
-                        for (int k = 0; k <= M; ++k) {
-                            const int c = (k < M) ? r->nbr[k] : cell;
-                            if (c >= 0) {
-                                const double4 cc = ldg_d4(P.c4 + c);
-                                const double dx = cc.x - pos.x, dy = cc.y - pos.y, dz = cc.z - pos.z;
-                                const double l = slow_sqrt(dx * dx + dy * dy + dz * dz);
-                                if (l < min_len) { min_len = l; best = c; }
-                            }
-                        }
-                    }
-#else
-                    const CellRec<M>* r = recs + cell;
-                    const int nv = r->nv;
                     double min_len = 1.7976931348623157e308;
                     int best = cell;
                     double len[M + 1]; // the candidates' distances: independent roots, one group
@@ -542,7 +662,6 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                         for (int k = 0; k <= M; ++k)
                             if (cand[k] >= 0 && len[k] < min_len) { min_len = len[k]; best = cand[k]; }
                     }
-#endif
                     if (best != cell) { cell = best; }
                     // walk mode: not limited to one ring (identical whenever the step is shorter than a cell)
                     if (EXTRA && P.walk) cell = walk_nearest<M>(recs, P.c4, cell, pos.x, pos.y, pos.z);
@@ -550,102 +669,34 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                 ++started;
                 if (P.cell_log) P.cell_log[pid * (long long)P.times + step] = P.c_int2ext[cell];
 
-                const CellRec<M>* __restrict__ rec = recs + cell;
-                const bool mono_f = P.sv[0].mono[cell] != 0;
-                const bool mono_b = PATH ? (P.sv[1].mono[cell] != 0) : false;
-                const double cur_depth = -1.0 * (double)depth_f;
-                const double alpha = PATH ? (double)step / (double)P.times : 0.0; // VK:1345
-                const double r = len3(pos);
-                d3 hvel = mk3(0.0, 0.0, 0.0);
-                double vvel = 0.0, at0 = 0.0, at1 = 0.0;
-                d3 new_pos;
-                EvalOut o;
-
-                // Euler = one stage, RK4 = four; all stages against the start-of-step cell
-                // (VK:931-957, R1).  One rolled loop => one inlined copy of the evaluation.
-                const int n_stage = P.use_euler ? 1 : 4;
-                d3 hprev = mk3(0.0, 0.0, 0.0);
-                int st = ST_ALIVE;
-#pragma unroll 1
-                for (int s = 0; s < n_stage; ++s) {
-                    d3 p = pos;
-                    double a_s = alpha;
-                    if (s > 0) {
-                        p = advect_on_sphere(pos, hprev, (s == 3) ? dt : dt * 0.5, r);
-                        if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
-                    }
-                    const CellRec<M>* __restrict__ rec_s = rec;
-                    bool mf = mono_f, mb = mono_b;
-                    if (EXTRA && P.walk && s > 0) { // MOPS_SEM_WALK: the cell that contains this stage point
-                        const int cs = walk_nearest<M>(recs, P.c4, cell, p.x, p.y, p.z);
-                        rec_s = recs + cs;
-                        mf = P.sv[0].mono[cs] != 0;
-                        mb = PATH ? (P.sv[1].mono[cs] != 0) : false;
-                    }
-                    if (EXTRA && P.diag_edge) {
-                        const double a = min_edge_angle<M>(rec_s, rec_s->nv, p.x, p.y, p.z);
-                        if (a < edge_min) edge_min = a;
-                    }
-                    // hexagon fast path: with nv == M every per-slot select of the evaluation folds away
-                    if (M == 6 && rec_s->nv == M) {
-                        st = PATH ? eval_path<M, true>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
-                                  : eval_stream<M, true>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
-                    } else {
-#if MOPS_COLD_GENERIC
-                        if (M == 6) { // the 12 pentagons (and coast cells) of a hexagonal mesh: out of line, so the hot code stays contiguous
-                            const EvalPacked r = eval_generic_cold<M, PATH>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p.x, p.y, p.z,
-                                                                            cur_depth, a_s, hint_f, hint_b);
-                            st = r.st; hint_f = r.hint_f; hint_b = r.hint_b; o = r.o;
-                        } else
-#endif
-                        st = PATH ? eval_path<M>(rec_s, P.sv, mf, mb, P.L, ATTR ? P.attr_count : 0, p, cur_depth, a_s, hint_f, hint_b, o)
-                                  : eval_stream<M>(rec_s, P.sv[0], mf, P.L, p, cur_depth, hint_f, o);
-                    }
-                    if (st != ST_ALIVE) break;
-                    if (s == 0) {
-                        hvel = mk3(o.hx, o.hy, o.hz);
-                        vvel = o.vv;
-                        if (ATTR) { at0 = o.a0; at1 = o.a1; }
-                    } else {
-                        const double c = (s == 3) ? 1.0 : 2.0; // s1 + 2 s2 + 2 s3 + s4, left to right (VK:959-960)
-                        hvel.x = hvel.x + c * o.hx;
-                        hvel.y = hvel.y + c * o.hy;
-                        hvel.z = hvel.z + c * o.hz;
-                        vvel = vvel + c * o.vv;
-                        if (ATTR) {
-                            at0 = at0 + c * o.a0;
-                            at1 = at1 + c * o.a1;
+                d3 hvel;
+                double at0 = 0.0, at1 = 0.0;
+                bool done = false;
+                if (FAST) {
+                    const CellRec<M>* __restrict__ rec = recs + cell;
+                    bool covered = (rec->nv == M) & (P.sv[0].mono[cell] != 0) & (P.use_euler == 0);
+                    if (PATH) covered = covered & (P.sv[1].mono[cell] != 0);
+                    if (covered) {
+                        const double alpha = PATH ? div_by((double)step, (double)P.times, x_times) : 0.0; // VK:1345 (exact: 1 <= times < 2^31)
+                        FastStep fs;
+                        const unsigned bad = fast_rk4_step<M, PATH, NOW>(rec, P.sv, P.L, pos, depth_f, alpha, dalpha_f, P.delta_t, hint_f, hint_b, fs);
+                        if (bad == 0u) {
+                            pos = fs.new_pos; hvel = fs.hvel; depth_f = fs.depth_f;
+                            done = true;
                         }
                     }
-                    hprev = mk3(o.hx, o.hy, o.hz);
                 }
-                if (st != ST_ALIVE) { status = st; break; }
-                if (P.use_euler) {
-                    new_pos = rotate_euler(pos, hvel, P.delta_t, r); // VK:968-972
-                } else {
-                    { // (s1 + 2 s2 + 2 s3 + s4) / 6.0: six quotients by one constant
-                        const double a6[6] = {hvel.x, hvel.y, hvel.z, vvel, at0, at1};
-                        double q6[6];
-                        bool ok6 = true;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) q6[i] = div_by6(a6[i], ok6);
-                        if (!ok6) {
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) q6[i] = slow_div(a6[i], 6.0);
-                        }
-                        hvel.x = q6[0]; hvel.y = q6[1]; hvel.z = q6[2];
-                        vvel = q6[3];
-                        at0 = q6[4]; at1 = q6[5];
-                    }
-                    const double tx = pos.x + hvel.x * dt, ty = pos.y + hvel.y * dt, tz = pos.z + hvel.z * dt; // VK:962-964
-                    const double tl = len3(tx, ty, tz);
-                    if (tl > 1e-12) {
-                        double ux, uy, uz;
-                        div3(tx, ty, tz, tl, ux, uy, uz);
-                        new_pos = mk3(ux * r, uy * r, uz * r);
-                    } else {
-                        new_pos = pos;
-                    }
+                if (!done) {
+                    StepIO io;
+                    io.pos = pos; io.hvel = mk3(0.0, 0.0, 0.0); io.at0 = 0.0; io.at1 = 0.0; io.edge_min = edge_min; io.depth_f = depth_f;
+                    io.hint_f = hint_f; io.hint_b = hint_b; io.status = ST_ALIVE;
+                    if (FAST) io = step_generic_cold<M, PATH, EXTRA, ATTR>(P, cell, step, io);
+                    else io = step_generic<M, PATH, EXTRA, ATTR>(P, cell, step, io);
+                    hint_f = io.hint_f; hint_b = io.hint_b;
+                    if (EXTRA) edge_min = io.edge_min;
+                    if (io.status != ST_ALIVE) { status = io.status; break; }
+                    pos = io.pos; hvel = io.hvel; depth_f = io.depth_f;
+                    if (ATTR) { at0 = io.at0; at1 = io.at1; }
                 }
 
                 if (first_vel) { // VK:988-991 / VK:1449-1456
@@ -653,22 +704,6 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                     st3(P.out_vel, base, hvel.x, hvel.y, hvel.z);
                     if (ATTR) st3(P.out_attr, base, at0, at1, 0.0);
                 }
-
-                // depth / radius update with the float round trip (VK:977-986, R3, R4)
-                const double old_depth = (double)depth_f;
-                double new_depth = old_depth - vvel * (double)P.delta_t;
-                new_depth = (0.0 < new_depth) ? new_depth : 0.0;
-                const double r_sum = r + vvel * (double)P.delta_t;
-                const double r_new = (1.0 < r_sum) ? r_sum : 1.0;
-                depth_f = (float)new_depth;
-                const double nlen = len3(new_pos);
-                if (nlen > 1e-12) {
-                    double ux, uy, uz;
-                    div3(new_pos.x, new_pos.y, new_pos.z, nlen, ux, uy, uz);
-                    new_pos = mk3(ux * r_new, uy * r_new, uz * r_new);
-                }
-                pos = new_pos;
-
                 bool rec_now;
                 if (PATH) rec_now = (P.record_interval > 0) && (((step + 1) % P.record_interval) == 0); // VK:1470-1471
                 else rec_now = (run_time % P.record_t) == 0;                                              // VK:994
@@ -682,7 +717,6 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                 }
             }
         }
-        (void)has_attr_out;
         P.pos[3 * pid] = pos.x; P.pos[3 * pid + 1] = pos.y; P.pos[3 * pid + 2] = pos.z;
         P.depth[pid] = depth_f;
         const bool park = SEG && status == ST_ALIVE && step_hi < P.times;
@@ -698,7 +732,7 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const AdvectPar
                 st3(P.out_vel, base + k, 0.0, 0.0, 0.0);
                 if (P.out_attr) st3(P.out_attr, base + k, 0.0, 0.0, 0.0);
             }
-            if (SEG) P.state[pid].alive = 0;
+            if (SEG && P.state) P.state[pid].alive = 0;
             if (P.status) P.status[pid] = status;
             if (P.steps) P.steps[pid] = started;
             if (P.fcell) P.fcell[pid] = (cell >= 0 && cell < P.nC) ? P.c_int2ext[cell] : -1;

@@ -19,6 +19,8 @@ for variant in ("rich", "nonmono"):
     a = eng.streamline(0, seeds, 600, 86400, 3600, depth=300.0, log_cells=True, near_edge=True)
     b = eng.pathline(0, 1, seeds, 600, 86400, 3600, depth=300.0, log_cells=True, walk=True)
     c = eng.streamline(0, seeds, 600, 86400, 3600, depth=300.0, method="euler", sort_particles=False)
+    d = eng.pathline(0, 1, seeds, 600, 86400, 3600, depth=300.0)  # production (SEG park/resume with MOPS_SEGMENT_STEPS=7)
+    e = eng.streamline(0, seeds, 600, 86400, 3600, depth=300.0)
     r = eng.remap(0, 64, 32, depth=300.0)
     v = eng.remap_fixed_layer(0, 64, 32, 3)
     g = eng.regrid_fixed_latitude(0, 64, 16, 20.0, 600.0, 5000.0)

@@ -119,31 +119,48 @@ def test_attribute_gating(ctx):
     assert img["img1"] is None and P.remap(m, P.prepare(m, a), 32, 16, depth=250.0)["img1"] is None
 
 
-@pytest.mark.parametrize("chunk", [257, 1000, 4999])
-def test_host_pipeline_chunks_match_single_pass(ctx, chunk, monkeypatch):
-    """HOST-mode calls above MOPS_HOST_CHUNK particles run as a three-stream chunk pipeline; every output
-    (records, attributes, cell log, status, steps, final cell, edge distance, end points, counters) must be
-    bit-identical to the single-pass call, for ragged last chunks, given and device-located start cells."""
+def test_host_submit_wait_matches_blocking_call(ctx):
+    """The asynchronous HOST-memory form (mops_*_submit / mops_traj_wait, two alternating staging sets): three calls in
+    flight back to back -- the third reuses the first one's staging set -- give, for every output (records, attributes,
+    cell log, status, steps, final cell, end points, counters), exactly what the blocking call gives; the what = 0 wait
+    returns the end points before the recorded trajectories have to be there; given and device-located start cells."""
+    import ctypes as C
     e, P, m, p0, p1, capi = ctx
     seeds = cases.seeds_random(5000, seed=21)
     seeds[17] = np.nan
     depths = np.linspace(5.0, 900.0, 5000).astype(np.float32)
     cells = P.locate(m, seeds)
     cells[40::97] = -1
+    n, dt, dur, rec = seeds.shape[0], 300, 21600, 3600
+    each, times = dur // rec, dur // dt
     for cell0 in (cells, None):
-        monkeypatch.delenv("MOPS_HOST_CHUNK", raising=False)
-        a = e.pathline(0, 1, seeds, 300, 21600, 3600, depths=depths, cell0=cell0, log_cells=True, near_edge=True)
-        monkeypatch.setenv("MOPS_HOST_CHUNK", str(chunk))
-        b = e.pathline(0, 1, seeds, 300, 21600, 3600, depths=depths, cell0=cell0, log_cells=True, near_edge=True)
-        for k in ("raw_pos", "raw_vel", "raw_attr", "pos", "depth", "cell_log", "status", "steps_alive", "final_cell", "min_edge"):
-            assert np.array_equal(a[k], b[k], equal_nan=True), k
-        for f in ("particle_steps", "alive_at_end", "near_edge_particles"):
-            assert int(getattr(a["stats"], f)) == int(getattr(b["stats"], f)), f
-        assert b["stats"].launches > a["stats"].launches and b["stats"].kernel_ms > 0
-    monkeypatch.setenv("MOPS_HOST_CHUNK", str(chunk))
-    s1 = e.streamline(0, seeds, 300, 21600, 1800, depth=300.0)
-    monkeypatch.delenv("MOPS_HOST_CHUNK")
-    s0 = e.streamline(0, seeds, 300, 21600, 1800, depth=300.0)
-    assert np.array_equal(s0["raw_pos"], s1["raw_pos"], equal_nan=True) and np.array_equal(s0["raw_vel"], s1["raw_vel"], equal_nan=True)
-    want = P.streamline(m, p0, seeds, P.locate(m, seeds), 300, 21600, 1800, depth=300.0)
-    assert np.array_equal(s1["raw_pos"], want["raw_pos"], equal_nan=True)
+        a = e.pathline(0, 1, seeds, dt, dur, rec, depths=depths, cell0=cell0, log_cells=True)
+        runs = []
+        for _ in range(3):
+            r = {"pos": seeds.copy(), "depth": depths.copy(), "raw_pos": np.full((n, each, 3), 7.0), "raw_vel": np.full((n, each, 3), 7.0),
+                 "raw_attr": np.full((n, each, 3), 7.0), "cell_log": np.zeros((n, times), np.int32), "status": np.zeros(n, np.int32),
+                 "steps_alive": np.zeros(n, np.int32), "final_cell": np.zeros(n, np.int32),
+                 "c0": None if cell0 is None else np.ascontiguousarray(cell0, dtype=np.int32)}
+            pt = lambda x: None if x is None else x.ctypes.data
+            r["io"] = capi.TrajIO(n, pt(r["pos"]), pt(r["depth"]), pt(r["c0"]), pt(r["raw_pos"]), pt(r["raw_vel"]), pt(r["raw_attr"]),
+                                  pt(r["cell_log"]), pt(r["status"]), pt(r["steps_alive"]), pt(r["final_cell"]), None)
+            runs.append(r)
+        cfg = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, dt, dur, rec, capi.MEM_HOST, 1)
+        tickets = [e.traj_submit(True, (0, 1), cfg, r["io"]) for r in runs]
+        assert tickets[0] > 0 and tickets[1] == tickets[0] + 1 and tickets[2] == tickets[0] + 2
+        e.traj_wait(tickets[1], 0)
+        assert np.array_equal(runs[1]["pos"], a["pos"], equal_nan=True) and np.array_equal(runs[1]["depth"], a["depth"])
+        for tk, r in zip(tickets, runs):
+            st = e.traj_wait(tk, 1)
+            for k in ("raw_pos", "raw_vel", "raw_attr", "pos", "depth", "cell_log", "status", "steps_alive", "final_cell"):
+                assert np.array_equal(a[k], r[k], equal_nan=True), k
+            if tk != tickets[0]:  # the first ticket's set was reused by the third submit, which completed it: its stats are gone
+                for f in ("particle_steps", "alive_at_end"):
+                    assert int(getattr(a["stats"], f)) == int(getattr(st, f)), f
+                assert st.kernel_ms > 0 and st.total_ms >= st.kernel_ms
+    # DEVICE-memory buffers have no submit form (they are asynchronous on the context's stream already)
+    cfg_d = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, dt, dur, rec, capi.MEM_DEVICE, 1)
+    with pytest.raises(capi.MopsError):
+        e.traj_submit(True, (0, 1), cfg_d, runs[0]["io"])
+    want = P.pathline(m, p0, p1, seeds, P.locate(m, seeds), dt, dur, rec, depths=depths)
+    assert np.array_equal(runs[2]["raw_pos"], want["raw_pos"], equal_nan=True)
