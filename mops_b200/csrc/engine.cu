@@ -451,17 +451,18 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
 // does not pay registers for either.  Resident 128-thread blocks per SM (register budget 65536 / (128 * MINB)):
 // 3 for the 6- and 8-wide records, 1 for the 20-wide ones -- from measurements on B200 (profiles/README.md:
 // 2 blocks 990 ms, 3 blocks 817 ms, 4 blocks 855 ms, 5 blocks 1065 ms, 6 blocks 1298 ms on the same step).
-template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false, bool NOW = false>
+template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false, bool NOW = false, bool FAST = false>
 void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 {
     const int grid = blocks_for(P.n, MOPS_ADV_BLOCK);
-    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR, SEG, NOW><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
+    k_advect<M, PATH, (M == 20 ? 1 : MOPS_ADV_MINB), EXTRA, ATTR, SEG, NOW, FAST><<<grid, MOPS_ADV_BLOCK, 0, ctx->stream>>>(P);
     ctx->launches++;
 }
 
-// Production launches always use the SEG instantiation (a single launch is the segment [0, times) with no parked state), the
-// EXTRA instantiations (walk semantics / near-edge diagnostic) are single-launch only.  now = neither snapshot carries
-// vertVelocityTop: hexagonal meshes (M == 6) then run the instantiation that does not accumulate the vertical sums.
+// Production launches always use the SEG instantiation (a single launch is the segment [0, times) with no parked state); the
+// EXTRA instantiations (walk semantics / near-edge diagnostic) are single-launch only.  Hexagonal meshes (M == 6) without
+// attributes run the FAST instantiations (straight-line RK4 step, fastpath.cuh), in the NOW form when neither snapshot
+// carries vertVelocityTop.
 template <int M>
 void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool now)
 {
@@ -470,16 +471,15 @@ void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool now)
     constexpr bool HEX = (M == 6);
     if (!path) {
         if (extra) launch_advect_inst<M, false, true, false>(ctx, P);
-        else if (HEX && now) launch_advect_inst<M, false, false, false, true, HEX>(ctx, P);
-        else launch_advect_inst<M, false, false, false, true>(ctx, P);
+        else if (HEX && now) launch_advect_inst<M, false, false, false, true, HEX, HEX>(ctx, P);
+        else launch_advect_inst<M, false, false, false, true, false, HEX>(ctx, P);
     } else if (attr) {
         if (extra) launch_advect_inst<M, true, true, true>(ctx, P);
-        else if (HEX && now) launch_advect_inst<M, true, false, true, true, HEX>(ctx, P);
         else launch_advect_inst<M, true, false, true, true>(ctx, P);
     } else {
         if (extra) launch_advect_inst<M, true, true, false>(ctx, P);
-        else if (HEX && now) launch_advect_inst<M, true, false, false, true, HEX>(ctx, P);
-        else launch_advect_inst<M, true, false, false, true>(ctx, P);
+        else if (HEX && now) launch_advect_inst<M, true, false, false, true, HEX, HEX>(ctx, P);
+        else launch_advect_inst<M, true, false, false, true, false, HEX>(ctx, P);
     }
 }
 

@@ -26,6 +26,10 @@
 #include "dmath.cuh"
 #include <stdint.h>
 
+#ifndef MOPS_EDGE_FROM_RECORD
+#define MOPS_EDGE_FROM_RECORD 0
+#endif
+
 namespace mops {
 
 // row offset (vertex id * L) into the vertex-major snapshot arrays: unsigned, so address arithmetic needs no sign word
@@ -159,7 +163,10 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
 }
 
 // Hexagon fast path of CalcPolygonWachspress (nv == M): the same quotients with three point-independent pieces removed.
-//  * the edge v_(k+1) - v_k of triangle_area comes from the record (computed by the same subtraction at mesh set-up);
+//  * (MOPS_EDGE_FROM_RECORD=1 only) the edge v_(k+1) - v_k of triangle_area comes from the record (computed by the same
+//    subtraction at mesh set-up).  Off by default: the kernel's second-tightest resource is the L1 -> register write-back
+//    path (128 B/clk/SM, ncu lsu_writeback_active 63 %), and 144 more loaded bytes per evaluation cost more there than the
+//    18 subtractions cost on the fp64 pipe;
 //  * the '/ 2.0' of the six triangle areas is dropped: scaling by a power of two commutes with rounding, so with
 //    a_k = 2 A_k every quotient is fl(B_i / (a_(i-1) a_i)) = w_i / 4 exactly, the sum is sum / 4, its reciprocal 4 / sum and
 //    the normalised weights (w_i / 4) * (4 / sum) are bit-identical to the reference's -- as long as nothing under- or
@@ -171,6 +178,7 @@ template <int M>
 __device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, double px, double py, double pz, double (&w)[M], bool& ok)
 {
     double a[M];
+#if MOPS_EDGE_FROM_RECORD
 #pragma unroll
     for (int k = 0; k < M; ++k) {
         const double e1x = rec->ex[k], e1y = rec->ey[k], e1z = rec->ez[k];
@@ -180,6 +188,18 @@ __device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, 
         const double cz = e1x * e2y - e1y * e2x;
         a[k] = cx * cx + cy * cy + cz * cz;
     }
+#else
+    {
+        double vx[M], vy[M], vz[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) { vx[k] = rec->vx[k]; vy[k] = rec->vy[k]; vz[k] = rec->vz[k]; }
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const int kn = (k + 1) % M;
+            a[k] = tri_cross2(vx[k], vy[k], vz[k], vx[kn], vy[kn], vz[kn], px, py, pz);
+        }
+    }
+#endif
     unsigned mn = hi_raw(a[0]), mx = mn;
 #pragma unroll
     for (int k = 1; k < M; ++k) {

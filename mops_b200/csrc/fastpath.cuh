@@ -20,6 +20,16 @@
 
 namespace mops {
 
+#ifndef MOPS_FAST_UNROLL_SNAP
+#define MOPS_FAST_UNROLL_SNAP 1
+#endif
+#ifndef MOPS_FAST_SPLIT_Z
+#define MOPS_FAST_SPLIT_Z 1
+#endif
+#ifndef MOPS_FAST_LOAD24
+#define MOPS_FAST_LOAD24 1
+#endif
+
 // exact x / 6.0 of the RK4 combine; flags anything outside the window in which the correction step is exact
 __device__ __forceinline__ double fast_div6(double a, unsigned& bad)
 {
@@ -103,16 +113,33 @@ __device__ __forceinline__ void fast_snapshot(const SnapView& s, const voff_t (&
     bad |= (unsigned)(h != hint);
     double top = 0.0, bot = 0.0;
     double dx = 0.0, dy = 0.0, dz = 0.0, dw = 0.0, ux = 0.0, uy = 0.0, uz = 0.0, uw = 0.0;
+#if MOPS_FAST_SPLIT_Z
+#pragma unroll
+    for (int i = 0; i < M; ++i) { // VK:774-781 for levels h-1, h, vertex order
+        const double* __restrict__ zq = s.ztop + (vo[i] + (voff_t)h);
+        top += w[i] * zq[-1];
+        bot += w[i] * zq[0];
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < M; ++i) { // VK:774-781 for levels h-1, h and TK:128-164 for the same two levels, vertex order
         const voff_t o = vo[i] + (voff_t)h;
+#if !MOPS_FAST_SPLIT_Z
         const double* __restrict__ zq = s.ztop + o;
-        const double4* __restrict__ q = s.velw + o;
         const double zt = zq[-1], zb = zq[0];
-        const double4 d = ldg_d4(q);
-        const double4 u = ldg_d4(q - 1);
         top += w[i] * zt;
         bot += w[i] * zb;
+#endif
+        const double4* __restrict__ q = s.velw + o;
+        double4 d, u;
+        if (NOW && MOPS_FAST_LOAD24) { // the w component is +0.0 and unused: 24-byte loads
+            ldg_d3of4(q, d.x, d.y, d.z);
+            ldg_d3of4(q - 1, u.x, u.y, u.z);
+            d.w = 0.0; u.w = 0.0;
+        } else {
+            d = ldg_d4(q);
+            u = ldg_d4(q - 1);
+        }
         dx += w[i] * d.x;
         dy += w[i] * d.y;
         dz += w[i] * d.z;
@@ -166,18 +193,27 @@ __device__ __forceinline__ void fast_eval(const CellRec<M>* __restrict__ rec, co
     voff_t vo[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) vo[i] = (voff_t)rec->vid[i] * (voff_t)L;
-    double fx, fy, fz, fw;
-    fast_snapshot<M, PATH, NOW>(sv[0], vo, w, L, depth, hint_f, fx, fy, fz, fw, bad);
     if (PATH) {
-        double bx, by, bz, bw;
-        fast_snapshot<M, PATH, NOW>(sv[1], vo, w, L, depth, hint_b, bx, by, bz, bw, bad);
+        // front and back through ONE rolled copy of the snapshot code (FAST_UNROLL_SNAP = 2 interleaves them: more
+        // independent chains, twice the gathered records in flight)
+        double fx = 0.0, fy = 0.0, fz = 0.0, fw = 0.0;
         const double oma = 1.0 - alpha;
-        hx = alpha * bx + oma * fx; // VK:1259
-        hy = alpha * by + oma * fy;
-        hz = alpha * bz + oma * fz;
-        vv = NOW ? 0.0 : alpha * bw + oma * fw; // VK:1286
+        constexpr int US = MOPS_FAST_UNROLL_SNAP;
+#pragma unroll US
+        for (int k = 0; k < 2; ++k) {
+            double bx, by, bz, bw;
+            fast_snapshot<M, PATH, NOW>(sv[k], vo, w, L, depth, k ? hint_b : hint_f, bx, by, bz, bw, bad);
+            if (k == 0) {
+                fx = bx; fy = by; fz = bz; fw = bw;
+            } else {
+                hx = alpha * bx + oma * fx; // VK:1259
+                hy = alpha * by + oma * fy;
+                hz = alpha * bz + oma * fz;
+                vv = NOW ? 0.0 : alpha * bw + oma * fw; // VK:1286
+            }
+        }
     } else {
-        hx = fx; hy = fy; hz = fz; vv = fw;
+        fast_snapshot<M, PATH, NOW>(sv[0], vo, w, L, depth, hint_f, hx, hy, hz, vv, bad);
         bad |= (unsigned)!(hx * hx + hy * hy + hz * hz >= 2.0e-24); // VK:850-852
     }
 }
@@ -209,8 +245,12 @@ __device__ __forceinline__ unsigned fast_rk4_step(const CellRec<M>* __restrict__
             p = fast_rotate(pos, hprev, (s == 3) ? dt : dt * 0.5, r, x_rr, bad);
             if (PATH) a_s = clamp01(alpha + ((s == 3) ? dalpha : 0.5 * dalpha)); // VK:1410-1424
         }
+        // the record is the same for the four stages: without this the compiler hoists all of its ~70 loads out of the stage
+        // loop and parks them in local memory (measured: 450 B of spills); re-reading them per stage hits L1
+        const CellRec<M>* __restrict__ rec_s = rec;
+        asm volatile("" : "+l"(rec_s));
         double hx, hy, hz, vv;
-        fast_eval<M, PATH, NOW>(rec, sv, L, p, cur_depth, a_s, hint_f, hint_b, hx, hy, hz, vv, bad);
+        fast_eval<M, PATH, NOW>(rec_s, sv, L, p, cur_depth, a_s, hint_f, hint_b, hx, hy, hz, vv, bad);
         if (s == 0) {
             acc = mk3(hx, hy, hz);
             vacc = vv;

@@ -385,7 +385,6 @@ __device__ __forceinline__ void st3(double* p, long long i, double x, double y, 
     p[3 * i] = x; p[3 * i + 1] = y; p[3 * i + 2] = z;
 }
 
-__device__ __forceinline__ double clamp01(double v) { return (v < 0.0) ? 0.0 : ((1.0 < v) ? 1.0 : v); }
 
 struct EvalPacked {
     EvalOut o;
