@@ -26,10 +26,6 @@
 #include "dmath.cuh"
 #include <stdint.h>
 
-#ifndef MOPS_EDGE_FROM_RECORD
-#define MOPS_EDGE_FROM_RECORD 0
-#endif
-
 namespace mops {
 
 // row offset (vertex id * L) into the vertex-major snapshot arrays: unsigned, so address arithmetic needs no sign word
@@ -45,7 +41,6 @@ struct alignas(32) CellRec {
     double vx[M], vy[M], vz[M]; // vertex positions
     double nx[M], ny[M], nz[M]; // cross(v_k, v_(k+1)%nv)                      (TK:45)
     double B[M];                // triangle_area(v_(i-1), v_i, v_(i+1))       (Interpolation.hpp:154)
-    double ex[M], ey[M], ez[M]; // v_(k+1)%nv - v_k: the point-independent edge of triangle_area(v_k, v_k+1, p) (Interpolation.hpp:100)
 };
 
 struct VertRec {      // per Voronoi vertex, mesh-constant part of the cell->vertex interpolation
@@ -162,11 +157,9 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
     wfinite = isfinite(sum) && isfinite(recp) && (sum > 0.0);
 }
 
-// Hexagon fast path of CalcPolygonWachspress (nv == M): the same quotients with three point-independent pieces removed.
-//  * (MOPS_EDGE_FROM_RECORD=1 only) the edge v_(k+1) - v_k of triangle_area comes from the record (computed by the same
-//    subtraction at mesh set-up).  Off by default: the kernel's second-tightest resource is the L1 -> register write-back
-//    path (128 B/clk/SM, ncu lsu_writeback_active 63 %), and 144 more loaded bytes per evaluation cost more there than the
-//    18 subtractions cost on the fp64 pipe;
+// Hexagon fast path of CalcPolygonWachspress (nv == M): the same quotients with two point-independent pieces removed.
+//    (keeping the edge v_(k+1) - v_k of triangle_area in the record was measured slower, profiles/r02_ab_fast2.txt: the L1
+//    data pipe is the kernel's second roof and 144 more loaded bytes per evaluation cost more than 18 subtractions);
 //  * the '/ 2.0' of the six triangle areas is dropped: scaling by a power of two commutes with rounding, so with
 //    a_k = 2 A_k every quotient is fl(B_i / (a_(i-1) a_i)) = w_i / 4 exactly, the sum is sum / 4, its reciprocal 4 / sum and
 //    the normalised weights (w_i / 4) * (4 / sum) are bit-identical to the reference's -- as long as nothing under- or
@@ -178,17 +171,6 @@ template <int M>
 __device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, double px, double py, double pz, double (&w)[M], bool& ok)
 {
     double a[M];
-#if MOPS_EDGE_FROM_RECORD
-#pragma unroll
-    for (int k = 0; k < M; ++k) {
-        const double e1x = rec->ex[k], e1y = rec->ey[k], e1z = rec->ez[k];
-        const double e2x = px - rec->vx[k], e2y = py - rec->vy[k], e2z = pz - rec->vz[k];
-        const double cx = e1y * e2z - e1z * e2y;
-        const double cy = e1z * e2x - e1x * e2z;
-        const double cz = e1x * e2y - e1y * e2x;
-        a[k] = cx * cx + cy * cy + cz * cz;
-    }
-#else
     {
         double vx[M], vy[M], vz[M];
 #pragma unroll
@@ -199,7 +181,6 @@ __device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, 
             a[k] = tri_cross2(vx[k], vy[k], vz[k], vx[kn], vy[kn], vz[kn], px, py, pz);
         }
     }
-#endif
     unsigned mn = hi_raw(a[0]), mx = mn;
 #pragma unroll
     for (int k = 1; k < M; ++k) {

@@ -29,14 +29,11 @@ __global__ void k_build_records(CellRec<M>* __restrict__ rec, int nC)
             r->ny[k] = az * bx - ax * bz;
             r->nz[k] = ax * by - ay * bx;
             r->B[k] = tri_area(r->vx[kp], r->vy[kp], r->vz[kp], ax, ay, az, bx, by, bz);
-            r->ex[k] = bx - ax; // e1 of triangle_area(v_k, v_k+1, p), Interpolation.hpp:100
-            r->ey[k] = by - ay;
-            r->ez[k] = bz - az;
         } else {
             r->nx[k] = 0.0; r->ny[k] = 0.0; r->nz[k] = 0.0; r->B[k] = 0.0;
-            r->ex[k] = 0.0; r->ey[k] = 0.0; r->ez[k] = 0.0;
         }
     }
+
 }
 
 // coefficients of GeoConverter::convertENUVelocityToXYZ (GeoConverter.hpp:225-250) at a cell

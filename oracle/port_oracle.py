@@ -210,6 +210,18 @@ def pixel_positions(width, height, lat_range=(-90.0, 90.0), lon_range=(-180.0, 1
     return out
 
 
+def pixel_positions_at(width, height, flat_index, lat_range=(-90.0, 90.0), lon_range=(-180.0, 180.0)) -> np.ndarray:
+    """sample points of the pixels with the given flat (row-major) indices"""
+    lib = _load()
+    idx = np.asarray(flat_index, dtype=np.int64)
+    out = np.zeros((idx.shape[0], 3))
+    tmp = np.zeros(3)
+    for k, f in enumerate(idx):
+        lib.orc_pixel_position(width, height, lat_range[0], lat_range[1], lon_range[0], lon_range[1], int(f // width), int(f % width), _p(tmp))
+        out[k] = tmp
+    return out
+
+
 def finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=False):
     lib = _load()
     n, each = raw_pos.shape[0], raw_pos.shape[1]

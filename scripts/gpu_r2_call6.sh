@@ -1,0 +1,8 @@
+# Round 2, call 6 (1 GPU): parity + A/B of the fast path with the in-cell filter taken from the Wachspress cross products
+set -x
+mkdir -p gpurun_out
+( MOPS_B200_LIB=$PWD/build_variants/fast3.so python -m pytest tests -m gpu -x -q ) 2>&1 | tail -8 | tee gpurun_out/r02_pytest_fast3.txt
+for f in build_variants/*.so; do
+  MOPS_B200_LIB=$PWD/$f timeout 200 python bench.py --level 8 --particles 16000000 --interval-steps 60 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary > gpurun_out/ab.log 2> gpurun_out/ab.err || { echo "$f FAILED"; tail -3 gpurun_out/ab.err; continue; }
+  tail -1 gpurun_out/ab.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$f', 'kernel_ms', round(d['roofline']['kernel_ms_per_launch'],2), 'value', round(d['value']/1e9,4), 'exec_frac', round(d['config']['executed_fraction'],4))"
+done 2>&1 | tee gpurun_out/r02_ab_fast3.txt
