@@ -412,13 +412,20 @@ def main():
     seeds_all = S.uniform_sphere_seeds(n_total, 20261018 + 5)
     if world > 1:
         all_dev = torch.from_numpy(seeds_all).to(dev)
-        key = eng.morton_rank(all_dev)
+        key = eng.order_key(all_dev).to(torch.int64) & 0xFFFFFFFF  # unsigned: -1 (no cell) sorts last, as in the engine
         order = torch.argsort(key, stable=True)
         lo, hi = sharding.block_bounds(n_total, rank, world)
-        perm = order[lo:hi].contiguous()
-        seeds0 = all_dev[perm].contiguous()
+        perm = order[lo:hi].to(torch.int32).contiguous()             # caller index of each local seed
+        seeds0 = all_dev[perm.long()].contiguous()
         del all_dev, key, order
         torch.cuda.empty_cache()
+        # NCCL communicator inside the library (the id travels over torch.distributed); the per-interval gather of the
+        # recorded trajectories + end points to rank 0, in caller order, is the product's mops_dist_gather_traj
+        uid = [eng.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.dist_create(rank, world, uid[0])
+        comm_stream = torch.cuda.Stream()
+        eng.dist_set_stream(comm_stream.cuda_stream)
     else:
         perm = None
         seeds0 = torch.from_numpy(seeds_all).to(dev)
@@ -430,12 +437,24 @@ def main():
 
     xyz = seeds0.clone()
     depth = torch.full((n,), DEPTH, dtype=torch.float32, device=dev)
-    out_pos = torch.empty((n, each, 3), dtype=torch.float64, device=dev)
-    out_vel = torch.empty((n, each, 3), dtype=torch.float64, device=dev)
     sort = 0 if args.no_sort else 1
     cfg = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, sort)
-    io = capi.TrajIO(n, xyz.data_ptr(), depth.data_ptr(), None, out_pos.data_ptr(), out_vel.data_ptr(), None, None, None, None, None)
+    # two output sets when N > 1: the gather of interval i (comm stream) overlaps the kernels of interval i+1
+    n_sets = 2 if world > 1 else 1
+    outs = [(torch.empty((n, each, 3), dtype=torch.float64, device=dev), torch.empty((n, each, 3), dtype=torch.float64, device=dev))
+            for _ in range(n_sets)]
+    ios = [capi.TrajIO(n, xyz.data_ptr(), depth.data_ptr(), None, o[0].data_ptr(), o[1].data_ptr(), None, None, None, None, None) for o in outs]
+    out_pos, out_vel = outs[0]
+    io = ios[0]
     counts = sharding.all_counts(n, world, device=dev)
+    if world > 1:
+        ends = [(torch.empty((n, 3), dtype=torch.float64, device=dev), torch.empty((n,), dtype=torch.float32, device=dev)) for _ in range(2)]
+        gathered = ([torch.empty((n_total, each, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+                    + [torch.empty((n_total, 3), dtype=torch.float64, device=dev), torch.empty((n_total,), dtype=torch.float32, device=dev)]
+                    if rank == 0 else [None] * 4)
+        k_done = [torch.cuda.Event() for _ in range(2)]
+        g_done = [torch.cuda.Event() for _ in range(2)]
+        g_used = [False, False]
     setup_s = time.perf_counter() - t_setup
 
     def reset_particles():
@@ -444,14 +463,23 @@ def main():
             depth.fill_(DEPTH)
 
     def one_step(i, io_, cfg_):
+        k = i % n_sets
+        if world > 1 and g_used[k]:
+            torch.cuda.current_stream().wait_event(g_done[k])  # output set k is free again once its gather has run
         reset_particles()
         # next snapshot: async H2D + device preprocessing on the side stream (double buffering)
         upload((i + 2) % 3, i + 2, True)
-        st = eng.traj_device(True, (i % 3, (i + 1) % 3), cfg_, io_, want_stats=True)
+        st = eng.traj_device(True, (i % 3, (i + 1) % 3), cfg_, ios[k] if io_ is io else io_, want_stats=True)
         if world > 1:
-            # the path's one exchange: end points gathered to rank 0 over NCCL/NVLink (the recorded trajectories follow the
-            # same route in the product's multi-GPU layer, mops_multi_*)
-            sharding.gather_rows(xyz, counts, rank, world, dst=0)
+            # the path's one exchange: recorded trajectories + end points to rank 0 in caller order, NCCL over NVLink
+            # (variable-size send/recv inside the library), on the comm stream so that it overlaps the next interval
+            ends[k][0].copy_(xyz); ends[k][1].copy_(depth)
+            k_done[k].record()
+            comm_stream.wait_event(k_done[k])
+            eng.dist_gather_traj(0, counts, perm, each, pos=outs[k][0], vel=outs[k][1], xyz=ends[k][0], depth=ends[k][1], n_total=n_total,
+                                 out_pos=gathered[0], out_vel=gathered[1], out_xyz=gathered[2], out_depth=gathered[3])
+            g_done[k].record(comm_stream)
+            g_used[k] = True
         return st
 
     def barrier():
@@ -557,6 +585,7 @@ def main():
     if not args.no_secondary:
         xyz.copy_(seeds0); depth.fill_(DEPTH)
         cfg_e = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, sort, 1)
+        torch.cuda.synchronize()
         st_e = eng.traj_device(True, (step_no % 3, (step_no + 1) % 3), cfg_e, io, want_stats=True)
         te = torch.tensor([float(st_e.near_edge_particles)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -617,8 +646,9 @@ def main():
                              "mesh+snapshots replicated",
               "snapshot_distribution": ("1/N PCIe upload per rank + NCCL all-gather" if use_ag
                                         else "whole snapshot uploaded by every rank")}
+    torch.cuda.synchronize()
     eng.close()
-    del xyz, depth, out_pos, out_vel, seeds0
+    del xyz, depth, out_pos, out_vel, outs, seeds0
     torch.cuda.empty_cache()
 
     # ---- CPU baseline + parity on its sample + remap figures (rank 0, N = 1 only) -----------------------------------

@@ -21,6 +21,7 @@
 #include <memory>
 #include <optional>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ---- vector types (24-byte vec3 with x()/y()/z() accessors, as every call site of the
@@ -65,7 +66,8 @@ using CartesianCoord = vec3;
 #define ONE_MONTH 60 * 60 * 24 * 30
 #define ONE_YEAR 60 * 60 * 24 * 30 * 12
 
-struct mops_ctx; // the engine context (include/mops_b200.h)
+struct mops_ctx;   // the engine context (include/mops_b200.h)
+struct mops_multi; // all devices of the box behind one handle (include/mops_b200.h)
 
 namespace MOPS {
 
@@ -286,10 +288,22 @@ public:
     ::mops_ctx* engine() const { return mCtx; } // the C-ABI context, for callers that want the flat API
     int locate(const std::vector<CartesianCoord>& pts, std::vector<int>& cells);
 
+    ::mops_multi* multi() const { return mMulti; } // non-null when more than one device is in use (MOPS_DEVICES / "gpu:<n>")
+
 private:
     int residentSlot(int solID);
+    int uploadSnapshot(int solID, int slot, bool async);
+    int pickSlot(int keepA, int keepB);
+    void prefetch(int solID);
+    void joinPrefetch();
     MOPSState mState = MOPSState::Uninitialized;
-    ::mops_ctx* mCtx = nullptr;
+    ::mops_ctx* mCtx = nullptr;      // device 0's context (every single-device call: views, point location)
+    ::mops_multi* mMulti = nullptr;  // all devices (trajectory calls shard over them)
+    std::thread mPreThread;          // background upload of the next snapshot of a chain
+    int mPreSol = -1, mPreRc = 0;
+    struct PinBuf { void* p = nullptr; size_t cap = 0; };
+    PinBuf mPinned[2];               // page-locked staging of the raw trajectory records (grow-only, reused by every call)
+    double* pinnedScratch(int which, size_t bytes);
     std::shared_ptr<MPASOGrid> mpasoGrid;
     std::map<int, std::shared_ptr<MPASOSolution>> mpasoAttributeMap;
     std::shared_ptr<MPASOField> mpasoField;

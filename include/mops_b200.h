@@ -264,6 +264,66 @@ int mops_remap_fixed_layer(mops_ctx* ctx, const mops_view_cfg* cfg, int32_t slot
 int mops_regrid_fixed_latitude(mops_ctx* ctx, const mops_view_cfg* cfg, int32_t slot, double* img, int32_t* pixel_cell,
                                mops_remap_stats* stats);
 
+/* ---- multi-GPU -------------------------------------------------------------------------------------
+ * Particles shard, the mesh and the resident snapshots are replicated on every GPU, there is no collective inside the
+ * time loop; the one exchange of the path is the gather of the recorded trajectories and end points to one owner, in
+ * caller order (lineID = input index, src/Common/TrajectoryCommon.h:47,124), over NCCL (NVLink / NVSwitch).  The
+ * reference has no counterpart: its only multi-rank code is a serial loop over MPI ranks in CLI/main.cpp:58-66,276-284.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return MOPS_E_STATE and the single-GPU ABI is unaffected. */
+
+/* Processing-order key of a point: the rank of its cell along the mesh's Morton curve (what the engine sorts particles
+ * by), -1 where the point has no cell.  Sharding = sort the seed set by this key and cut it into equal contiguous blocks
+ * (mops_shard_bounds): equal counts for ANY seed distribution, spatially compact working set per GPU. */
+int mops_order_key(mops_ctx* ctx, int32_t mem, int64_t n, const double* xyz, int32_t* key_out);
+void mops_shard_bounds(int64_t n_total, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+void* mops_get_stream(mops_ctx* ctx); /* the cudaStream_t the context's kernels run on */
+int mops_get_device(mops_ctx* ctx);
+
+/* One process per GPU (torchrun, MPI ...): rank 0 obtains an id (mops_dist_unique_id, 128 bytes = ncclUniqueId), the caller
+ * broadcasts it by its own means, every rank calls mops_dist_create with its context (collective). */
+typedef struct mops_dist mops_dist;
+#define MOPS_DIST_ID_BYTES 128
+int mops_dist_unique_id(void* id128);
+int mops_dist_create(mops_dist** out, mops_ctx* ctx, int32_t rank, int32_t world, const void* id128);
+void mops_dist_destroy(mops_dist* d);
+const char* mops_dist_last_error(const mops_dist* d);
+/* run the gathers on a caller-owned cudaStream_t instead of the context's stream (NULL restores it), e.g. to overlap the
+ * exchange of interval i with the kernels of interval i+1; ordering against the kernels is then the caller's (events) */
+int mops_dist_set_stream(mops_dist* d, void* cuda_stream);
+/* Collective.  Every rank contributes n_local = counts[rank] particles: index[i] = caller (global) index of local particle i,
+ * pos / vel = [n_local][each][3] records, xyz = [n_local][3] end points, depth = [n_local] (any of the four may be NULL on
+ * all ranks).  On `root` the rows land at their caller index in out_pos / out_vel [n_total][each][3], out_xyz [n_total][3],
+ * out_depth [n_total].  All pointers are DEVICE pointers; variable-size ncclSend / ncclRecv in one group, enqueued on
+ * the context's stream (asynchronous: order later work after it on that stream). */
+int mops_dist_gather_traj(mops_dist* d, int32_t root, int64_t n_local, const int64_t* counts, const int32_t* index, int32_t each,
+                          const double* pos, const double* vel, const double* xyz, const float* depth, int64_t n_total,
+                          double* out_pos, double* out_vel, double* out_xyz, float* out_depth);
+
+/* One process, N GPUs: N contexts + one host thread per device behind one handle (n_devices <= 0: every device of the box;
+ * devices = NULL: ordinals 0..n-1).  Mesh and snapshots are replicated (each device pulls a snapshot over its own PCIe link,
+ * in parallel); a trajectory call takes HOST buffers in caller order, sorts the seeds along the mesh's Morton curve on
+ * device 0, cuts N equal contiguous blocks, ships each block to its device over NCCL, integrates the blocks concurrently
+ * and gathers records / end points / status back to device 0 in caller order over NCCL (mops_dist_gather_traj's routine)
+ * before the copy to the caller's buffers -- results are identical to the single-device call, whatever N.  This is what the
+ * C++ drop-in's MOPS_RunStreamLine / MOPS_RunPathLine run on when more than one device is selected (MOPS_DEVICES=<n>).
+ * Pixel views (remap, fixed layer / latitude) and point location run on mops_multi_ctx(m, 0). */
+typedef struct mops_multi mops_multi;
+int mops_multi_create(mops_multi** out, int32_t n_devices, const int32_t* devices);
+void mops_multi_destroy(mops_multi* m);
+const char* mops_multi_last_error(const mops_multi* m);
+int32_t mops_multi_device_count(const mops_multi* m);
+mops_ctx* mops_multi_ctx(mops_multi* m, int32_t i);
+int mops_multi_set_mesh(mops_multi* m, int32_t n_cells, int32_t n_vertices, int32_t max_edges, const double* cell_xyz,
+                        const double* vertex_xyz, const int32_t* vertices_on_cell, const int32_t* cells_on_cell,
+                        const int32_t* cells_on_vertex, const int32_t* n_edges_on_cell);
+int mops_multi_set_snapshot(mops_multi* m, int32_t slot, int32_t n_levels, const double* zonal, const double* meridional,
+                            const double* layer_thickness, const double* bottom_depth, const double* vert_vel_top,
+                            int32_t n_attr, const double* const* attrs, int32_t n_attr_total, int32_t async);
+int mops_multi_snapshot_wait(mops_multi* m, int32_t slot);
+int mops_multi_streamline(mops_multi* m, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io, mops_traj_stats* stats);
+int mops_multi_pathline(mops_multi* m, const mops_traj_cfg* cfg, int32_t front_slot, int32_t back_slot, const mops_traj_io* io,
+                        mops_traj_stats* stats);
+
 /* ---- introspection ---------------------------------------------------------------- */
 typedef struct mops_info {
     int32_t device, sm_count, cc_major, cc_minor;

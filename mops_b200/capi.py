@@ -30,7 +30,10 @@ ABI_SYMBOLS = [
     "mops_abi_version", "mops_create", "mops_destroy", "mops_last_error", "mops_host_alloc", "mops_host_free",
     "mops_synchronize", "mops_set_stream", "mops_mark", "mops_elapsed_ms", "mops_set_mesh", "mops_set_snapshot", "mops_set_snapshot_async", "mops_snapshot_wait", "mops_side_wait_event",
     "mops_get_prepared", "mops_locate", "mops_streamline", "mops_pathline", "mops_streamline_submit", "mops_pathline_submit",
-    "mops_traj_wait", "mops_finalize_lines",
+    "mops_traj_wait", "mops_finalize_lines", "mops_order_key", "mops_shard_bounds", "mops_get_stream", "mops_get_device",
+    "mops_dist_unique_id", "mops_dist_create", "mops_dist_destroy", "mops_dist_last_error", "mops_dist_set_stream", "mops_dist_gather_traj",
+    "mops_multi_create", "mops_multi_destroy", "mops_multi_last_error", "mops_multi_device_count", "mops_multi_ctx",
+    "mops_multi_set_mesh", "mops_multi_set_snapshot", "mops_multi_snapshot_wait", "mops_multi_streamline", "mops_multi_pathline",
     "mops_remap_fixed_depth", "mops_remap_fixed_layer", "mops_regrid_fixed_latitude", "mops_get_info",
 ]
 
@@ -115,6 +118,33 @@ def load_library():
     lib.mops_streamline_submit.argtypes = [vp, C.POINTER(TrajCfg), i32, C.POINTER(TrajIO), C.POINTER(i64)]
     lib.mops_pathline_submit.argtypes = [vp, C.POINTER(TrajCfg), i32, i32, C.POINTER(TrajIO), C.POINTER(i64)]
     lib.mops_traj_wait.argtypes = [vp, i64, i32, C.POINTER(TrajStats)]
+    lib.mops_order_key.argtypes = [vp, i32, i64, vp, vp]
+    lib.mops_shard_bounds.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.mops_shard_bounds.restype = None
+    lib.mops_get_stream.argtypes = [vp]
+    lib.mops_get_stream.restype = vp
+    lib.mops_get_device.argtypes = [vp]
+    lib.mops_dist_unique_id.argtypes = [vp]
+    lib.mops_dist_create.argtypes = [C.POINTER(vp), vp, i32, i32, vp]
+    lib.mops_dist_destroy.argtypes = [vp]
+    lib.mops_dist_destroy.restype = None
+    lib.mops_dist_last_error.argtypes = [vp]
+    lib.mops_dist_last_error.restype = C.c_char_p
+    lib.mops_dist_set_stream.argtypes = [vp, vp]
+    lib.mops_dist_gather_traj.argtypes = [vp, i32, i64, C.POINTER(i64), vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp]
+    lib.mops_multi_create.argtypes = [C.POINTER(vp), i32, vp]
+    lib.mops_multi_destroy.argtypes = [vp]
+    lib.mops_multi_destroy.restype = None
+    lib.mops_multi_last_error.argtypes = [vp]
+    lib.mops_multi_last_error.restype = C.c_char_p
+    lib.mops_multi_device_count.argtypes = [vp]
+    lib.mops_multi_ctx.argtypes = [vp, i32]
+    lib.mops_multi_ctx.restype = vp
+    lib.mops_multi_set_mesh.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.mops_multi_set_snapshot.argtypes = snap_args + [i32]
+    lib.mops_multi_snapshot_wait.argtypes = [vp, i32]
+    lib.mops_multi_streamline.argtypes = [vp, C.POINTER(TrajCfg), i32, C.POINTER(TrajIO), C.POINTER(TrajStats)]
+    lib.mops_multi_pathline.argtypes = [vp, C.POINTER(TrajCfg), i32, i32, C.POINTER(TrajIO), C.POINTER(TrajStats)]
     lib.mops_finalize_lines.argtypes = [i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.mops_remap_fixed_depth.argtypes = [vp, C.POINTER(RemapCfg), i32, vp, vp, vp, C.POINTER(RemapStats)]
     lib.mops_remap_fixed_layer.argtypes = [vp, C.POINTER(ViewCfg), i32, vp, vp, C.POINTER(RemapStats)]
@@ -161,9 +191,10 @@ class Engine:
         self._keep = []
 
     def close(self):
-        if getattr(self, "h", None):
+        self.dist_close()
+        if getattr(self, "h", None) and not getattr(self, "_borrowed", False):
             self.lib.mops_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -251,6 +282,52 @@ class Engine:
         out = torch.empty(xyz.shape[0], dtype=torch.int32, device=xyz.device)
         self._ck(self.lib.mops_locate(self.h, MEM_DEVICE, xyz.shape[0], _ptr(xyz), _ptr(out)))
         return out
+
+    def order_key(self, xyz):
+        """rank of each point's cell along the mesh's Morton curve (what the engine sorts particles by); -1 = no cell"""
+        if isinstance(xyz, np.ndarray):
+            xyz = _np(xyz, np.float64)
+            out = np.zeros(xyz.shape[0], dtype=np.int32)
+            self._ck(self.lib.mops_order_key(self.h, MEM_HOST, xyz.shape[0], _ptr(xyz), _ptr(out)))
+            return out
+        import torch
+        out = torch.empty(xyz.shape[0], dtype=torch.int32, device=xyz.device)
+        self._ck(self.lib.mops_order_key(self.h, MEM_DEVICE, xyz.shape[0], _ptr(xyz), _ptr(out)))
+        return out
+
+    # ---- one process per GPU: NCCL communicator inside the library ----------------------------
+    def dist_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.mops_dist_unique_id(buf)
+        if rc != 0:
+            raise MopsError(f"mops_dist_unique_id -> {rc} (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def dist_create(self, rank: int, world: int, unique_id: bytes):
+        h = C.c_void_p()
+        rc = self.lib.mops_dist_create(C.byref(h), self.h, rank, world, C.create_string_buffer(unique_id, 128))
+        if rc != 0:
+            raise MopsError(f"mops_dist_create(rank={rank}, world={world}) -> {rc}")
+        self.dist = h
+        return h
+
+    def dist_gather_traj(self, root, counts, index, each, pos=None, vel=None, xyz=None, depth=None, n_total=0,
+                         out_pos=None, out_vel=None, out_xyz=None, out_depth=None):
+        """device tensors in, caller-order device tensors out on `root` (see include/mops_b200.h); asynchronous on the stream"""
+        cnt = (C.c_int64 * len(counts))(*[int(c) for c in counts])
+        n_local = int(index.shape[0])
+        rc = self.lib.mops_dist_gather_traj(self.dist, root, n_local, cnt, _ptr(index), each, _ptr(pos), _ptr(vel), _ptr(xyz), _ptr(depth),
+                                            n_total, _ptr(out_pos), _ptr(out_vel), _ptr(out_xyz), _ptr(out_depth))
+        if rc != 0:
+            raise MopsError(f"mops_dist_gather_traj -> {rc}: {self.lib.mops_dist_last_error(self.dist).decode()}")
+
+    def dist_set_stream(self, cuda_stream):
+        self._ck(self.lib.mops_dist_set_stream(self.dist, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def dist_close(self):
+        if getattr(self, "dist", None):
+            self.lib.mops_dist_destroy(self.dist)
+            self.dist = None
 
     # ---- trajectories ----------------------------------------------------------------------
     def _traj(self, path, slots, seeds, delta_t, duration, record_t, depth, depths, cell0, method, direction,
@@ -359,3 +436,89 @@ class Engine:
         self._ck(self.lib.mops_remap_fixed_depth(self.h, C.byref(cfg), slot, _ptr(img0), _ptr(img1), _ptr(cells),
                                                  C.byref(st) if want_stats else None))
         return st
+
+
+class MultiEngine:
+    """One process, N GPUs (mops_multi_*): mesh + snapshots replicated, trajectory calls shard their seeds over the devices
+    and come back in caller order.  `.dev0` is an Engine view of device 0's context (views, point location)."""
+
+    def __init__(self, n_devices: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.mops_multi_create(C.byref(self.h), n_devices, None)
+        if rc != 0:
+            raise MopsError(f"mops_multi_create({n_devices}) failed with {rc} (devices / NCCL missing; there is no CPU fallback)")
+        self.n = int(self.lib.mops_multi_device_count(self.h))
+        self.dev0 = Engine.__new__(Engine)
+        self.dev0.lib = self.lib
+        self.dev0.h = C.c_void_p(self.lib.mops_multi_ctx(self.h, 0))
+        self.dev0._borrowed = True
+        self.dev0.levels = {}
+        self.dev0._keep = []
+        self.dev0.mesh = None
+        self.levels = {}
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MopsError(f"[{rc}] {self.lib.mops_multi_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mops_multi_destroy(self.h)
+            self.h = None
+            self.dev0.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mesh(self, mesh):
+        arrs = (_np(mesh.cell_xyz, np.float64), _np(mesh.vertex_xyz, np.float64), _np(mesh.vertices_on_cell, np.int32),
+                _np(mesh.cells_on_cell, np.int32), _np(mesh.cells_on_vertex, np.int32), _np(mesh.n_edges_on_cell, np.int32))
+        self._ck(self.lib.mops_multi_set_mesh(self.h, mesh.n_cells, mesh.n_vertices, mesh.max_edges, *[_ptr(a) for a in arrs]))
+        self.mesh = mesh
+        self.dev0.mesh = mesh
+
+    def set_snapshot(self, slot: int, snap, async_: bool = False):
+        names = sorted(snap.attrs.keys())
+        arrs = [_np(snap.attrs[n], np.float64) for n in names[:2]]
+        pa = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+        ins = (_np(snap.zonal, np.float64), _np(snap.meridional, np.float64), _np(snap.layer_thickness, np.float64),
+               _np(snap.bottom_depth, np.float64), _np(snap.vert_vel_top, np.float64))
+        self._ck(self.lib.mops_multi_set_snapshot(self.h, slot, snap.n_levels, *[_ptr(a) for a in ins], len(arrs), pa, len(names),
+                                                  1 if async_ else 0))
+        if async_:
+            self._ck(self.lib.mops_multi_snapshot_wait(self.h, slot))
+        self.levels[slot] = snap.n_levels
+        self.dev0.levels[slot] = snap.n_levels
+
+    def _traj(self, path, slots, seeds, delta_t, duration, record_t, depth=0.0, depths=None, cell0=None, method="rk4",
+              direction="forward", want_attr=False):
+        seeds = np.array(seeds, dtype=np.float64, order="C", copy=True)
+        n = seeds.shape[0]
+        each = int(duration) // int(record_t) if record_t else 0
+        dep = np.array(depths, dtype=np.float32, copy=True) if depths is not None else np.full(n, depth, dtype=np.float32)
+        out_pos = np.full((n, max(each, 0), 3), 7.0); out_vel = np.full((n, max(each, 0), 3), 7.0)
+        out_attr = np.full((n, max(each, 0), 3), 7.0) if want_attr else None
+        status = np.zeros(n, dtype=np.int32); steps = np.zeros(n, dtype=np.int32); fcell = np.zeros(n, dtype=np.int32)
+        c0 = _np(cell0, np.int32)
+        cfg = TrajCfg(METHOD_RK4 if method == "rk4" else METHOD_EULER, DIR_FORWARD if direction == "forward" else DIR_BACKWARD,
+                      int(delta_t), int(duration), int(record_t), MEM_HOST, 1, 0, SEM_REFERENCE)
+        io = TrajIO(n, _ptr(seeds), _ptr(dep), _ptr(c0), _ptr(out_pos), _ptr(out_vel), _ptr(out_attr), None,
+                    _ptr(status), _ptr(steps), _ptr(fcell), None)
+        st = TrajStats()
+        if path:
+            rc = self.lib.mops_multi_pathline(self.h, C.byref(cfg), slots[0], slots[1], C.byref(io), C.byref(st))
+        else:
+            rc = self.lib.mops_multi_streamline(self.h, C.byref(cfg), slots[0], C.byref(io), C.byref(st))
+        self._ck(rc)
+        return {"raw_pos": out_pos, "raw_vel": out_vel, "raw_attr": out_attr, "pos": seeds, "depth": dep,
+                "status": status, "steps_alive": steps, "final_cell": fcell, "stats": st}
+
+    def streamline(self, slot, seeds, delta_t, duration, record_t, **kw):
+        return self._traj(False, (slot, slot), seeds, delta_t, duration, record_t, **kw)
+
+    def pathline(self, front, back, seeds, delta_t, duration, record_t, **kw):
+        return self._traj(True, (front, back), seeds, delta_t, duration, record_t, **kw)

@@ -10,6 +10,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,7 +59,7 @@ struct mops_ctx {
     bool l2_attr_valid = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_kend = nullptr, ev_end = nullptr;
     std::string err;
-    long long launches = 0;
+    std::atomic<long long> launches{0}; // kernels launched (a snapshot upload may run on a second host thread, see mops_set_snapshot_async)
 
     // mesh
     bool has_mesh = false;
@@ -764,7 +765,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     CK(cudaEventRecord(S.out_done, so));
     S.busy = true;
     S.ticket = tk;
-    S.launches = ctx->launches - launches0;
+    S.launches = ctx->launches.load() - launches0;
     if (ticket) {
         *ticket = tk;
         return MOPS_OK;
@@ -1280,6 +1281,33 @@ int mops_locate(mops_ctx* ctx, int32_t mem, int64_t n, const double* xyz, int32_
     return MOPS_OK;
 }
 
+int mops_order_key(mops_ctx* ctx, int32_t mem, int64_t n, const double* xyz, int32_t* key_out)
+{
+    if (!ctx) return MOPS_E_INVALID;
+    if (!ctx->has_mesh) return fail(ctx, MOPS_E_STATE, "no mesh");
+    if (n < 0 || (n > 0 && (!xyz || !key_out))) return fail(ctx, MOPS_E_INVALID, "bad order-key arguments");
+    if (n == 0) return MOPS_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    // the engine numbers its cells along a Morton curve, so the internal id of a point's cell IS its rank on the curve
+    if (mem == MOPS_MEM_HOST) {
+        if ((rc = ensure(ctx, ctx->p_xyz, (size_t)n * 24))) return rc;
+        if ((rc = ensure(ctx, ctx->p_cell0, (size_t)n * 4))) return rc;
+        CK(cudaMemcpyAsync(ctx->p_xyz.p, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+        dispatch_locate(ctx, n, (const double*)ctx->p_xyz.p, (int*)ctx->p_cell0.p, nullptr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(key_out, ctx->p_cell0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        dispatch_locate(ctx, n, xyz, key_out, nullptr);
+        CK(cudaGetLastError());
+    }
+    return MOPS_OK;
+}
+
+void* mops_get_stream(mops_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int mops_get_device(mops_ctx* ctx) { return ctx ? ctx->device : -1; }
+
 int mops_streamline(mops_ctx* ctx, const mops_traj_cfg* cfg, int32_t slot, const mops_traj_io* io, mops_traj_stats* stats)
 {
     return trajectory_impl(ctx, cfg, slot, slot, io, stats, false, nullptr);
@@ -1495,7 +1523,7 @@ int mops_get_info(mops_ctx* ctx, mops_info* out)
         if (ctx->snap[i].valid) out->n_levels = ctx->snap[i].L;
     }
     out->record_width = ctx->M;
-    out->total_launches = ctx->launches;
+    out->total_launches = ctx->launches.load();
     return MOPS_OK;
 }
 

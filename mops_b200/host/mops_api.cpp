@@ -10,11 +10,13 @@
 #include <signal.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <memory>
 #include <mutex>
@@ -192,7 +194,10 @@ MOPSApp app;
 MOPSApp::MOPSApp() = default;
 MOPSApp::~MOPSApp()
 {
-    if (mCtx) mops_destroy(mCtx);
+    if (mPreThread.joinable()) mPreThread.join();
+    for (auto& b : mPinned) if (b.p) mops_host_free(b.p);
+    if (mMulti) mops_multi_destroy(mMulti); // owns every context, device 0's included
+    else if (mCtx) mops_destroy(mCtx);
 }
 
 namespace {
@@ -219,10 +224,22 @@ void MOPSApp::init(const char* device)
         std::printf("Device requested: cpu -- this build has no CPU path; using the CUDA device\n");
     int dev = 0;
     if (const char* e = std::getenv("MOPS_DEVICE")) dev = std::atoi(e);
+    // more than one GPU: MOPS_Init("gpu:<n>") / MOPS_Init("gpu:all") or MOPS_DEVICES=<n>|all.  Trajectory calls then shard their
+    // seeds over the devices (mops_multi_*: Morton blocks, NCCL gather in caller order); results do not depend on <n>.
+    int n_multi = 1;
+    const char* spec = (device && std::strncmp(device, "gpu:", 4) == 0) ? device + 4 : std::getenv("MOPS_DEVICES");
+    if (spec && *spec) n_multi = (std::strcmp(spec, "all") == 0) ? 0 : std::atoi(spec);
     if (!mCtx) {
-        const int rc = mops_create(&mCtx, dev);
+        int rc;
+        if (n_multi != 1) {
+            rc = mops_multi_create(&mMulti, n_multi, nullptr);
+            if (rc == MOPS_OK) mCtx = mops_multi_ctx(mMulti, 0);
+        } else {
+            rc = mops_create(&mCtx, dev);
+        }
         if (rc != MOPS_OK) {
-            std::fprintf(stderr, " [ MOPS: no usable CUDA device (mops_create -> %d); there is no CPU fallback ]\n", rc);
+            std::fprintf(stderr, " [ MOPS: no usable CUDA device%s (-> %d); there is no CPU fallback ]\n",
+                         n_multi != 1 ? "s / NCCL for the multi-GPU form" : "", rc);
             std::exit(1);
         }
     }
@@ -231,6 +248,7 @@ void MOPSApp::init(const char* device)
     mops_get_info(mCtx, &info);
     std::printf("Device selected : CUDA device %d (sm_%d%d, %d SMs) -- B200-native engine\n", info.device, info.cc_major, info.cc_minor,
                 info.sm_count);
+    if (mMulti) std::printf("Devices in use  : %d (particles shard over them; mesh and snapshots replicated)\n", mops_multi_device_count(mMulti));
     std::printf("MOPS Version    : mops-b200 (ABI %d)\n", mops_abi_version());
     std::fflush(stdout);
     mpasoGrid = std::make_shared<MPASOGrid>();
@@ -258,9 +276,13 @@ void MOPSApp::addGrid(std::shared_ptr<MPASOGrid> grid)
     };
     const auto voc = narrow(g.verticesOnCell_vec, nC * E), coc = narrow(g.cellsOnCell_vec, nC * E),
                cov = narrow(g.cellsOnVertex_vec, nV * 3), ne = narrow(g.numberVertexOnCell_vec, nC);
-    const int rc = mops_set_mesh(mCtx, g.mCellsSize, g.mVertexSize, g.mMaxEdgesSize, reinterpret_cast<const double*>(g.cellCoord_vec.data()),
-                                 reinterpret_cast<const double*>(g.vertexCoord_vec.data()), voc.data(), coc.data(), cov.data(), ne.data());
+    joinPrefetch();
+    const int rc = mMulti ? mops_multi_set_mesh(mMulti, g.mCellsSize, g.mVertexSize, g.mMaxEdgesSize, reinterpret_cast<const double*>(g.cellCoord_vec.data()),
+                                                reinterpret_cast<const double*>(g.vertexCoord_vec.data()), voc.data(), coc.data(), cov.data(), ne.data())
+                          : mops_set_mesh(mCtx, g.mCellsSize, g.mVertexSize, g.mMaxEdgesSize, reinterpret_cast<const double*>(g.cellCoord_vec.data()),
+                                          reinterpret_cast<const double*>(g.vertexCoord_vec.data()), voc.data(), coc.data(), cov.data(), ne.data());
     if (rc != MOPS_OK) {
+        if (mMulti) std::fprintf(stderr, "[MOPS/b200] addGrid: %s\n", mops_multi_last_error(mMulti));
         engine_error(mCtx, "addGrid", rc);
         std::exit(1);
     }
@@ -294,30 +316,28 @@ void MOPSApp::addField()
     mHasBack = false;
 }
 
-// make `solID` resident in one of the engine's snapshot slots (LRU over MOPS_MAX_SNAPSHOT_SLOTS)
-int MOPSApp::residentSlot(int solID)
+// a snapshot slot for a new resident: a free one, else the least recently used that is neither keepA nor keepB
+int MOPSApp::pickSlot(int keepA, int keepB)
 {
-    auto touch = [&](int slot) {
-        for (size_t i = 0; i < mSlotOrder.size(); ++i)
-            if (mSlotOrder[i] == slot) { mSlotOrder.erase(mSlotOrder.begin() + i); break; }
-        mSlotOrder.push_back(slot);
-    };
-    auto it = mSlotOf.find(solID);
-    if (it != mSlotOf.end()) {
-        touch(it->second);
-        return it->second;
-    }
-    int slot = -1;
     if (static_cast<int>(mSlotOf.size()) < MOPS_MAX_SNAPSHOT_SLOTS) {
         std::vector<bool> used(MOPS_MAX_SNAPSHOT_SLOTS, false);
         for (auto& kv : mSlotOf) used[kv.second] = true;
         for (int s = 0; s < MOPS_MAX_SNAPSHOT_SLOTS; ++s)
-            if (!used[s]) { slot = s; break; }
-    } else {
-        slot = mSlotOrder.front();
+            if (!used[s]) return s;
+    }
+    for (int slot : mSlotOrder) {
+        if (slot == keepA || slot == keepB) continue;
         for (auto kv = mSlotOf.begin(); kv != mSlotOf.end(); ++kv)
             if (kv->second == slot) { mSlotOf.erase(kv); break; }
+        return slot;
     }
+    return -1;
+}
+
+// upload + device preprocessing of `solID` into `slot` (replaces the reference's host preprocessing chain of addSol,
+// src/Core/MOPSApp.cpp:100-130); async = enqueue on the engine's side stream and return
+int MOPSApp::uploadSnapshot(int solID, int slot, bool async)
+{
     const MPASOSolution& s = *mpasoAttributeMap.at(solID);
     const size_t nC = static_cast<size_t>(mpasoGrid->mCellsSize), L = static_cast<size_t>(s.mVertLevels);
     if (s.cellZonalVelocity_vec.size() < nC * L || s.cellMeridionalVelocity_vec.size() < nC * L ||
@@ -332,11 +352,68 @@ int MOPSApp::residentSlot(int solID)
         if (kv.second.size() >= nC * L) attrs.push_back(kv.second.data());
     }
     const double* wtop = s.cellVertVelocity_vec.size() >= nC * (L + 1) ? s.cellVertVelocity_vec.data() : nullptr;
+    const int n_attr = static_cast<int>(attrs.size()), n_total = static_cast<int>(s.mDoubleAttributes.size());
+    const double* const* ap = attrs.empty() ? nullptr : attrs.data();
+    if (mMulti)
+        return mops_multi_set_snapshot(mMulti, slot, s.mVertLevels, s.cellZonalVelocity_vec.data(), s.cellMeridionalVelocity_vec.data(),
+                                       s.cellLayerThickness_vec.data(), s.cellBottomDepth_vec.data(), wtop, n_attr, ap, n_total, async ? 1 : 0);
+    return async ? mops_set_snapshot_async(mCtx, slot, s.mVertLevels, s.cellZonalVelocity_vec.data(), s.cellMeridionalVelocity_vec.data(),
+                                           s.cellLayerThickness_vec.data(), s.cellBottomDepth_vec.data(), wtop, n_attr, ap, n_total)
+                 : mops_set_snapshot(mCtx, slot, s.mVertLevels, s.cellZonalVelocity_vec.data(), s.cellMeridionalVelocity_vec.data(),
+                                     s.cellLayerThickness_vec.data(), s.cellBottomDepth_vec.data(), wtop, n_attr, ap, n_total);
+}
+
+void MOPSApp::joinPrefetch()
+{
+    if (mPreThread.joinable()) mPreThread.join();
+    if (mPreSol >= 0 && mPreRc != MOPS_OK) {
+        engine_error(mCtx, "snapshot prefetch", mPreRc);
+        std::exit(1);
+    }
+    mPreSol = -1;
+}
+
+// Chained pathlines (tutorial/pathLine.cpp:250-296 of the reference advance a front/back pair per interval): while the
+// interval (a, b) integrates, the snapshot that follows b in the attribute map is uploaded and preprocessed in the
+// background -- a host thread feeds the engine's side stream (the source arrays are pageable std::vectors, so the staging
+// copies block that thread, not the caller), the kernels of the running call are untouched because the target slot is
+// neither a's nor b's.  The next MOPS_ActiveAttribute then finds it resident.
+void MOPSApp::prefetch(int solID)
+{
+    if (std::getenv("MOPS_NO_PREFETCH")) return;
+    if (mSlotOf.count(solID) || !mpasoAttributeMap.count(solID)) return;
+    joinPrefetch();
+    const int keepA = mSlotOf.count(mFrontID) ? mSlotOf[mFrontID] : -1, keepB = (mHasBack && mSlotOf.count(mBackID)) ? mSlotOf[mBackID] : -1;
+    const int slot = pickSlot(keepA, keepB);
+    if (slot < 0) return;
+    mSlotOf[solID] = slot;
+    mSlotOrder.erase(std::remove(mSlotOrder.begin(), mSlotOrder.end(), slot), mSlotOrder.end());
+    mSlotOrder.insert(mSlotOrder.begin(), slot); // least recently used until it is activated
+    mPreSol = solID;
+    mPreRc = MOPS_OK;
+    mPreThread = std::thread([this, solID, slot] { mPreRc = uploadSnapshot(solID, slot, true); });
+}
+
+// make `solID` resident in one of the engine's snapshot slots (LRU over MOPS_MAX_SNAPSHOT_SLOTS)
+int MOPSApp::residentSlot(int solID)
+{
+    auto touch = [&](int slot) {
+        for (size_t i = 0; i < mSlotOrder.size(); ++i)
+            if (mSlotOrder[i] == slot) { mSlotOrder.erase(mSlotOrder.begin() + i); break; }
+        mSlotOrder.push_back(slot);
+    };
+    if (mPreSol == solID) joinPrefetch(); // its upload is enqueued; the engine orders the first use after it
+    auto it = mSlotOf.find(solID);
+    if (it != mSlotOf.end()) {
+        touch(it->second);
+        return it->second;
+    }
+    joinPrefetch();
+    const int slot = pickSlot(-1, -1);
     Scope sc("Preprocessing::snapshot", 2);
-    const int rc = mops_set_snapshot(mCtx, slot, s.mVertLevels, s.cellZonalVelocity_vec.data(), s.cellMeridionalVelocity_vec.data(),
-                                     s.cellLayerThickness_vec.data(), s.cellBottomDepth_vec.data(), wtop, static_cast<int>(attrs.size()),
-                                     attrs.empty() ? nullptr : attrs.data(), static_cast<int>(s.mDoubleAttributes.size()));
+    const int rc = uploadSnapshot(solID, slot, false);
     if (rc != MOPS_OK) {
+        if (mMulti) std::fprintf(stderr, "[MOPS/b200] set_snapshot: %s\n", mops_multi_last_error(mMulti));
         engine_error(mCtx, "set_snapshot", rc);
         std::exit(1);
     }
@@ -365,11 +442,29 @@ void MOPSApp::activeAttribute(int ID1, std::optional<int> ID2)
         mFrontID = ID1; mBackID = ID2.value(); mHasBack = true;
         residentSlot(mFrontID);
         residentSlot(mBackID);
+        auto nxt = mpasoAttributeMap.upper_bound(mBackID); // the pair a chain activates next is (back, the one after it)
+        if (nxt != mpasoAttributeMap.end()) prefetch(nxt->first);
     } else {
         mpasoField->mSol_Front = it->second;
         mFrontID = ID1; mHasBack = false;
         residentSlot(mFrontID);
     }
+}
+
+// page-locked scratch for the raw records, kept between calls (pinning is slow -- ~1 GB/s -- so a chain of intervals pins
+// once); small requests are not worth it and use pageable memory
+double* MOPSApp::pinnedScratch(int which, size_t bytes)
+{
+    if (bytes < (64u << 20) || std::getenv("MOPS_NO_PINNED")) return nullptr;
+    PinBuf& b = mPinned[which];
+    if (bytes > b.cap) {
+        if (b.p) mops_host_free(b.p);
+        b.p = nullptr; b.cap = 0;
+        void* p = nullptr;
+        if (mops_host_alloc(&p, bytes) != MOPS_OK) return nullptr;
+        b.p = p; b.cap = bytes;
+    }
+    return static_cast<double*>(b.p);
 }
 
 int MOPSApp::locate(const std::vector<CartesianCoord>& pts, std::vector<int>& cells)
@@ -390,8 +485,12 @@ std::vector<float> effective_depths(const TrajectorySettings* cfg, size_t n)
     return std::vector<float>(n, cfg->depth);
 }
 
-std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, int slot_b, TrajectorySettings* config,
-                                      std::vector<CartesianCoord>& seeds, const char* what)
+// raw_pos / raw_vel: caller-provided staging for the flat records ([n][each][3] doubles each), page-locked when the caller
+// could get it (the D2H then runs at PCIe speed instead of through the driver's bounce buffer); multi != nullptr shards the
+// call over every device
+std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, ::mops_multi* multi, bool path, int slot_f, int slot_b, TrajectorySettings* config,
+                                      std::vector<CartesianCoord>& seeds, const char* what,
+                                      const std::function<double*(int, size_t)>& scratch)
 {
     std::vector<TrajectoryLine> lines;
     if (config == nullptr || seeds.empty()) return lines; // VK:659-665
@@ -421,7 +520,13 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, in
     std::vector<CartesianCoord> pos = seeds; // stable_points
     // the engine writes every slot of both buffers (zeros for the slots a stopped particle never reaches), so they are
     // not value-initialised here: at 1 M seeds x 168 records that alone would be 8 GB of serial zero-fill
-    std::unique_ptr<double[]> raw_pos(new double[n * each * 3]), raw_vel(new double[n * each * 3]);
+    std::unique_ptr<double[]> own_pos, own_vel;
+    double* raw_pos = scratch(0, n * each * 3 * sizeof(double));
+    double* raw_vel = scratch(1, n * each * 3 * sizeof(double));
+    if (!raw_pos || !raw_vel) { // no page-locked memory to be had: pageable buffers work too
+        own_pos.reset(new double[n * each * 3]); own_vel.reset(new double[n * each * 3]);
+        raw_pos = own_pos.get(); raw_vel = own_vel.get();
+    }
     mops_traj_cfg cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.method = (config->methodType == CalcMethodType::kEuler) ? MOPS_METHOD_EULER : MOPS_METHOD_RK4;
@@ -437,11 +542,14 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, in
     io.xyz = reinterpret_cast<double*>(pos.data());
     io.depth = depths.data();
     io.cell0 = nullptr; // located on the device (replaces MPASOField::calcInWhichCells)
-    io.out_pos = raw_pos.get();
-    io.out_vel = raw_vel.get();
+    io.out_pos = raw_pos;
+    io.out_vel = raw_vel;
     mops_traj_stats st;
-    const int rc = path ? mops_pathline(ctx, &cfg, slot_f, slot_b, &io, &st) : mops_streamline(ctx, &cfg, slot_f, &io, &st);
+    int rc;
+    if (multi) rc = path ? mops_multi_pathline(multi, &cfg, slot_f, slot_b, &io, &st) : mops_multi_streamline(multi, &cfg, slot_f, &io, &st);
+    else rc = path ? mops_pathline(ctx, &cfg, slot_f, slot_b, &io, &st) : mops_streamline(ctx, &cfg, slot_f, &io, &st);
     if (rc != MOPS_OK) {
+        if (multi) std::fprintf(stderr, "[MOPS/b200] %s: %s\n", what, mops_multi_last_error(multi));
         engine_error(ctx, what, rc);
         return lines;
     }
@@ -449,7 +557,7 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, bool path, int slot_f, in
     book().add(std::string("MemoryCopy::") + what, 3, st.total_ms - st.kernel_ms - st.locate_ms);
 
     // line assembly + NaN trimming (TrajectoryCommon.h:43-190) on the flat buffers
-    lines = detail::assemble_lines(n, each, seeds.data(), raw_pos.get(), raw_vel.get(), path, static_cast<double>(config->simulationDuration),
+    lines = detail::assemble_lines(n, each, seeds.data(), raw_pos, raw_vel, path, static_cast<double>(config->simulationDuration),
                                    static_cast<double>(config->deltaT), depths0.data());
     return lines;
 }
@@ -462,7 +570,8 @@ std::vector<TrajectoryLine> MOPSApp::runStreamLine(TrajectorySettings* config, s
         std::fprintf(stderr, "[MOPSApp]::mpasoField is nullptr, please activeAttribute first\n");
         return {};
     }
-    return run_lines(mCtx, false, residentSlot(mFrontID), -1, config, sample_points, "StreamLine");
+    return run_lines(mCtx, mMulti, false, residentSlot(mFrontID), -1, config, sample_points, "StreamLine",
+                     [this](int w, size_t b) { return pinnedScratch(w, b); });
 }
 
 std::vector<TrajectoryLine> MOPSApp::runPathLine(TrajectorySettings* config, std::vector<CartesianCoord>& sample_points)
@@ -477,7 +586,7 @@ std::vector<TrajectoryLine> MOPSApp::runPathLine(TrajectorySettings* config, std
         std::exit(-1);
     }
     const int sf = residentSlot(mFrontID), sb = residentSlot(mBackID);
-    auto lines = run_lines(mCtx, true, sf, sb, config, sample_points, "PathLine");
+    auto lines = run_lines(mCtx, mMulti, true, sf, sb, config, sample_points, "PathLine", [this](int w, size_t b) { return pinnedScratch(w, b); });
     // the caller's seeds become each line's lastPoint (src/Core/MOPSApp.cpp:287-290, R14)
     for (size_t i = 0; i < sample_points.size() && i < lines.size(); ++i) sample_points[i] = lines[i].lastPoint;
     return lines;

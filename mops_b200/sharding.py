@@ -1,8 +1,9 @@
 """Particle sharding for the multi-GPU path: particles are independent, the mesh
-and the resident snapshots are replicated on every GPU, each rank owns a spatially compact
-block of particles (a longitude sector), and the only exchange is the gather of results to
-rank 0 at the end of an interval.  Host-side logic only (torch.distributed does the plumbing:
-NCCL on GPUs, gloo in the CPU tests)."""
+and the resident snapshots are replicated on every GPU, each rank owns an equal, spatially compact
+block of the seed set sorted along the mesh's Morton curve, and the only exchange is the gather of
+results to one owner at the end of an interval (in the product: mops_dist_gather_traj / mops_multi_*,
+NCCL inside the library).  Host-side logic only; torch.distributed does the bench's plumbing (NCCL on
+GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
 from typing import List, Optional, Tuple
@@ -22,6 +23,23 @@ def shard_seeds(xyz: np.ndarray, rank: int, world: int) -> Tuple[np.ndarray, np.
         return xyz, np.arange(xyz.shape[0], dtype=np.int64)
     idx = np.nonzero(longitude_sector(xyz, world) == rank)[0]
     return np.ascontiguousarray(xyz[idx]), idx
+
+
+def block_bounds(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of rank's block when n_total key-sorted seeds are cut into `world` equal contiguous blocks (the first
+    n_total % world blocks hold one more) -- the Python twin of mops_shard_bounds (include/mops_b200.h)"""
+    world = max(world, 1)
+    base, extra = divmod(int(n_total), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def morton_blocks(keys: np.ndarray, world: int) -> List[np.ndarray]:
+    """caller indices of every rank's block: a stable sort of the seed set by processing-order key (the rank of each
+    seed's cell along the mesh's Morton curve, mops_order_key), cut by block_bounds.  Equal counts for ANY seed
+    distribution; each block is a spatially compact range of the curve."""
+    order = np.argsort(np.asarray(keys).astype(np.uint32), kind="stable")  # -1 (no cell) sorts last, as on the device
+    return [order[slice(*block_bounds(order.shape[0], r, world))] for r in range(max(world, 1))]
 
 
 def all_counts(n_local: int, world: int, device=None) -> List[int]:

@@ -22,7 +22,7 @@ def _lib():
 def test_exports_match_header():
     lib, capi = _lib()
     hdr = open(os.path.join(ROOT, "include", "mops_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|void|const char\*)\s+(mops_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|void|const char\*|void\*|int32_t|mops_ctx\*)\s+(mops_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
     assert declared == set(capi.ABI_SYMBOLS), declared ^ set(capi.ABI_SYMBOLS)
     raw = ctypes.CDLL(capi.LIB_PATH)
     for name in declared:
