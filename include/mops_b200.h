@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MOPS_B200_ABI_VERSION 1
+#define MOPS_B200_ABI_VERSION 2
 
 typedef struct mops_ctx mops_ctx;
 
@@ -171,7 +171,8 @@ typedef struct mops_traj_io {
     const int32_t* cell0;   /* [n] start cells or NULL (then located on the device)           */
     double* out_pos;        /* [n][each][3] recorded positions, each = duration / record_t    */
     double* out_vel;        /* [n][each][3] recorded velocities                               */
-    double* out_attr;       /* [n][each][3] pathline attributes (x,y used) or NULL            */
+    double* out_attr;       /* [n][each][3] pathline attributes (x,y used) or NULL; written only when the snapshots
+                               carry attributes (n_attr_total > 1, VK:1093-1104), otherwise left untouched       */
     int32_t* out_cell_log;  /* [n][steps] cell of every step (-1 = not executed) or NULL      */
     int32_t* out_status;    /* [n] MOPS_ST_* or NULL                                          */
     int32_t* out_steps;     /* [n] steps started (alive at step start) or NULL                */
@@ -188,6 +189,9 @@ typedef struct mops_traj_stats {
     int32_t launches;       /* kernels of this library launched by the call                   */
     int32_t reserved;
     int64_t near_edge_particles; /* particles that came within 1e-12 rad of a cell edge (count_near_edge) */
+    int64_t above_surface_particles; /* pathline: particles stopped with MOPS_ST_ABOVE_SURFACE -- the depth lies above the
+                                        interpolated sea surface (negative zTop[0]) and the reference would read
+                                        ztop[-1] there (VK:1225, undefined behaviour); they keep their last position */
 } mops_traj_stats;
 
 /* Both calls integrate in launches of 40 steps (environment MOPS_SEGMENT_STEPS=<n>, 0 = one launch) with the

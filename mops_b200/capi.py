@@ -53,7 +53,7 @@ class TrajIO(C.Structure):
 class TrajStats(C.Structure):
     _fields_ = [("particle_steps", C.c_int64), ("alive_at_end", C.c_int64), ("kernel_ms", C.c_double),
                 ("locate_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_int32), ("reserved", C.c_int32),
-                ("near_edge_particles", C.c_int64)]
+                ("near_edge_particles", C.c_int64), ("above_surface_particles", C.c_int64)]
 
 
 class RemapCfg(C.Structure):

@@ -466,6 +466,7 @@ int multi_traj(mops_multi* mm, const mops_traj_cfg* cfg, int front, int back, co
             stats->particle_steps += st[g].particle_steps;
             stats->alive_at_end += st[g].alive_at_end;
             stats->near_edge_particles += st[g].near_edge_particles;
+            stats->above_surface_particles += st[g].above_surface_particles;
             stats->kernel_ms = std::max(stats->kernel_ms, st[g].kernel_ms);
             stats->locate_ms = std::max(stats->locate_ms, st[g].locate_ms);
             stats->total_ms = std::max(stats->total_ms, st[g].total_ms);

@@ -348,7 +348,7 @@ struct AdvectParams {
     double* min_edge; // or null: per-particle smallest edge distance [rad] (diagnostic)
     int diag_edge;    // 1 = track the smallest edge distance of every evaluated point
     int walk;         // 1 = MOPS_SEM_WALK: evaluate each stage point in the cell that contains it
-    unsigned long long* counters; // [0] particle-steps started, [1] alive at end, [3] near-edge particles
+    unsigned long long* counters; // [0] particle-steps started, [1] alive at end, [3] near-edge particles, [4] stopped above the surface
     // segmented launches (SEG instantiations only): one launch integrates steps [step_begin, step_end) of the call;
     // particles still alive at step_end < times park their loop state in `state`, and the host compacts `order`
     // to the live ones before the next segment, so lanes of stopped particles do not ride along to the end.
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const __grid_co
 {
     static_assert(!FAST || (M == 6 && !EXTRA && !ATTR), "the straight-line path is the hexagon / no-attribute / no-diagnostic form");
     const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long my_steps = 0, my_alive = 0, my_near = 0;
+    unsigned long long my_steps = 0, my_alive = 0, my_near = 0, my_above = 0;
     const long long n_act = (SEG && P.n_live) ? (long long)*P.n_live : P.n;
     if (tix < n_act) {
         const long long pid = P.order ? (long long)P.order[tix] : tix;
@@ -735,6 +735,7 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const __grid_co
             if (EXTRA && P.min_edge) P.min_edge[pid] = edge_min;
             my_alive = (status == ST_ALIVE) ? 1ull : 0ull;
             my_near = (EXTRA && P.diag_edge && edge_min < 1e-12) ? 1ull : 0ull;
+            my_above = (PATH && status == ST_ABOVE_SURFACE) ? 1ull : 0ull;
         }
         my_steps = (unsigned long long)(started - started0);
     }
@@ -744,11 +745,13 @@ __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const __grid_co
         my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
         my_alive += __shfl_xor_sync(0xffffffffu, my_alive, off);
         my_near += __shfl_xor_sync(0xffffffffu, my_near, off);
+        if (PATH) my_above += __shfl_xor_sync(0xffffffffu, my_above, off);
     }
     if ((threadIdx.x & 31) == 0 && P.counters) {
         atomicAdd(P.counters + 0, my_steps);
         atomicAdd(P.counters + 1, my_alive);
         if (my_near) atomicAdd(P.counters + 3, my_near);
+        if (PATH && my_above) atomicAdd(P.counters + 4, my_above);
     }
 }
 

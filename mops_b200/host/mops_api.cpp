@@ -553,6 +553,9 @@ std::vector<TrajectoryLine> run_lines(::mops_ctx* ctx, ::mops_multi* multi, bool
         engine_error(ctx, what, rc);
         return lines;
     }
+    if (st.above_surface_particles > 0) // N2: the reference reads ztop[-1] for these (undefined behaviour); here they stop and keep their last position
+        std::fprintf(stderr, "[B200::%s] %lld particle(s) stopped above the interpolated sea surface (depth < -zTop[0])\n", what,
+                     static_cast<long long>(st.above_surface_particles));
     book().add(std::string("GPUKernel::") + what + "::kernel", 4, st.kernel_ms);
     book().add(std::string("MemoryCopy::") + what, 3, st.total_ms - st.kernel_ms - st.locate_ms);
 

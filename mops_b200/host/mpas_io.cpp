@@ -188,9 +188,14 @@ int type_size(int t)
 struct Cursor {
     FILE* f;
     int version;
+    uint64_t file_size; // every length read from the header is checked against it: a malformed file cannot make us allocate or seek past it
     void need(void* dst, size_t n)
     {
         if (std::fread(dst, 1, n, f) != n) throw std::runtime_error("netcdf: truncated header");
+    }
+    void skip(uint64_t n)
+    {
+        if (n > file_size || fseeko(f, static_cast<off_t>(n), SEEK_CUR) != 0) throw std::runtime_error("netcdf: truncated header");
     }
     uint32_t u32() { unsigned char b[4]; need(b, 4); return static_cast<uint32_t>(be(b, 4)); }
     uint64_t u64() { unsigned char b[8]; need(b, 8); return be(b, 8); }
@@ -199,10 +204,11 @@ struct Cursor {
     std::string name()
     {
         const uint64_t n = nonneg();
+        if (n > file_size || n > (1u << 20)) throw std::runtime_error("netcdf: implausible name length in the header");
         std::string s(n, '\0');
         if (n) need(&s[0], n);
         const uint64_t pad = (4 - n % 4) % 4;
-        if (pad) std::fseek(f, static_cast<long>(pad), SEEK_CUR);
+        if (pad) skip(pad);
         return s;
     }
     void skip_att_list()
@@ -215,9 +221,10 @@ struct Cursor {
             (void)name();
             const uint32_t t = u32();
             const uint64_t ne = nonneg();
+            if (ne > file_size) throw std::runtime_error("netcdf: implausible attribute length in the header");
             uint64_t bytes = ne * static_cast<uint64_t>(type_size(static_cast<int>(t)));
             bytes += (4 - bytes % 4) % 4;
-            std::fseek(f, static_cast<long>(bytes), SEEK_CUR);
+            skip(bytes);
         }
     }
 };
@@ -244,7 +251,14 @@ NcFile::NcFile(const std::string& path) : path_(path)
 {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("netcdf: cannot open " + path);
-    fp_ = f;
+    // the destructor does not run when this constructor throws: close the file on every exit path but the normal one
+    struct Guard {
+        FILE* f;
+        ~Guard() { if (f) std::fclose(f); }
+    } guard{f};
+    if (fseeko(f, 0, SEEK_END) != 0) throw std::runtime_error("netcdf: cannot seek in " + path);
+    const uint64_t file_size = static_cast<uint64_t>(ftello(f));
+    if (fseeko(f, 0, SEEK_SET) != 0) throw std::runtime_error("netcdf: cannot seek in " + path);
     unsigned char magic[4];
     if (std::fread(magic, 1, 4, f) != 4) throw std::runtime_error("netcdf: empty file " + path);
     if (magic[0] == 0x89 && magic[1] == 'H' && magic[2] == 'D' && magic[3] == 'F')
@@ -253,7 +267,7 @@ NcFile::NcFile(const std::string& path) : path_(path)
     if (magic[0] != 'C' || magic[1] != 'D' || magic[2] != 'F' || (magic[3] != 1 && magic[3] != 2 && magic[3] != 5))
         throw std::runtime_error("netcdf: " + path + " is not a NetCDF-3 file");
     version_ = magic[3];
-    Cursor c{f, version_};
+    Cursor c{f, version_, file_size};
     numrecs_ = c.nonneg();
     // dimensions
     {
@@ -261,6 +275,7 @@ NcFile::NcFile(const std::string& path) : path_(path)
         const uint64_t n = c.nonneg();
         if (!(tag == 0 && n == 0)) {
             if (tag != 0x0A) throw std::runtime_error("netcdf: bad dimension list tag");
+            if (n > file_size) throw std::runtime_error("netcdf: implausible dimension count");
             for (uint64_t i = 0; i < n; ++i) {
                 std::string nm = c.name();
                 const uint64_t len = c.nonneg();
@@ -276,11 +291,17 @@ NcFile::NcFile(const std::string& path) : path_(path)
         const uint64_t n = c.nonneg();
         if (!(tag == 0 && n == 0)) {
             if (tag != 0x0B) throw std::runtime_error("netcdf: bad variable list tag");
+            if (n > file_size) throw std::runtime_error("netcdf: implausible variable count");
             for (uint64_t i = 0; i < n; ++i) {
                 NcVar v;
                 v.name = c.name();
                 const uint64_t nd = c.nonneg();
-                for (uint64_t d = 0; d < nd; ++d) v.dimids.push_back(static_cast<int>(c.nonneg()));
+                if (nd > 1024) throw std::runtime_error("netcdf: implausible rank of variable " + v.name);
+                for (uint64_t d = 0; d < nd; ++d) {
+                    const uint64_t id = c.nonneg();
+                    if (id >= dims_.size()) throw std::runtime_error("netcdf: variable " + v.name + " names a dimension that does not exist");
+                    v.dimids.push_back(static_cast<int>(id));
+                }
                 c.skip_att_list();
                 v.type = static_cast<int>(c.u32());
                 v.vsize = c.nonneg();
@@ -300,13 +321,15 @@ NcFile::NcFile(const std::string& path) : path_(path)
         for (auto& v : vars_)
             if (v.is_record) recsize_ = v.elems_per_record * static_cast<uint64_t>(type_size(v.type));
     if (numrecs_ == 0xFFFFFFFFull && version_ != 5 && recsize_ > 0) { // STREAMING: derive from the file size
-        std::fseek(f, 0, SEEK_END);
-        const uint64_t size = static_cast<uint64_t>(std::ftell(f));
+        const uint64_t size = file_size;
         uint64_t first = UINT64_MAX;
         for (auto& v : vars_)
             if (v.is_record) first = std::min(first, v.begin);
         numrecs_ = first < size ? (size - first) / recsize_ : 0;
     }
+    fp_ = f;
+    file_size_ = file_size;
+    guard.f = nullptr; // ownership passes to the object
 }
 
 NcFile::~NcFile()
@@ -339,6 +362,9 @@ bool NcFile::read_as(const std::string& name, int64_t record, std::vector<T>& ou
     FILE* f = static_cast<FILE*>(fp_);
     const uint64_t per = v->elems_per_record;
     auto read_block = [&](uint64_t offset, uint64_t count) {
+        // sizes come from the header: never allocate or read beyond what the file can hold
+        if (offset > file_size_ || count > (file_size_ - offset) / static_cast<uint64_t>(ts))
+            throw std::runtime_error("netcdf: variable " + name + " extends past the end of " + path_);
         std::vector<unsigned char> buf(count * ts);
         if (fseeko(f, static_cast<off_t>(offset), SEEK_SET) != 0 || std::fread(buf.data(), 1, buf.size(), f) != buf.size())
             throw std::runtime_error("netcdf: short read of " + name + " in " + path_);

@@ -59,6 +59,7 @@ private:
     template <class T> bool read_as(const std::string& name, int64_t record, std::vector<T>& out) const;
     std::string path_;
     void* fp_ = nullptr;
+    uint64_t file_size_ = 0;
     int version_ = 1;
     uint64_t numrecs_ = 0, recsize_ = 0;
     std::vector<std::pair<std::string, uint64_t>> dims_;

@@ -27,7 +27,7 @@ def test_exports_match_header():
     raw = ctypes.CDLL(capi.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert raw.mops_abi_version() == 1
+    assert raw.mops_abi_version() == 2
 
 
 def test_no_cpu_fallback():

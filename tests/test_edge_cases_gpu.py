@@ -82,6 +82,8 @@ def test_depth_above_surface_and_below_bottom(ctx):
     gp = e.pathline(0, 1, seeds[:50], 600, 7200, 3600, depths=up, cell0=cells[:50])
     wp = P.pathline(m, p0, p1, seeds[:50], cells[:50], 600, 7200, 3600, depths=up)
     assert (gp["status"] == 5).all() and np.array_equal(gp["status"], wp["status"])
+    # ... and the count is surfaced (the C++ drop-in prints it): silent freezes near the surface were an advisor finding
+    assert int(gp["stats"].above_surface_particles) == gp["status"].shape[0]
 
 
 def test_record_periods(ctx):

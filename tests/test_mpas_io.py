@@ -70,3 +70,33 @@ def test_hdf5_file_is_rejected_with_a_reason(pyMOPS, tmp_path):
             % (os.path.join(ROOT, "tools", "pyMOPS"), yaml))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode != 0 and "netCDF-4/HDF5" in r.stderr
+
+
+@pytest.mark.parametrize("damage", ["truncated_header", "bad_dimension_id", "huge_name", "truncated_data"])
+def test_malformed_netcdf_fails_with_a_message_not_a_crash(pyMOPS, tmp_path, damage):
+    """the header parser does not trust the file: lengths are checked against the file size, dimension ids against
+    the dimension list, and the reader exits with a message (the reference's reader aborts the process as well)"""
+    m = cases.mesh(2)
+    snaps = [S.solid_body_snapshot(m, 4, 0.5)]
+    yaml = S.write_mpas_files(str(tmp_path), m, snaps)
+    path = os.path.join(str(tmp_path), "mesh.nc")
+    raw = bytearray(open(path, "rb").read())
+    if damage == "truncated_header":
+        raw = raw[:40]
+    elif damage == "truncated_data":
+        raw = raw[: len(raw) // 2]
+    elif damage == "huge_name":
+        raw[16:20] = (0x7FFFFFF0).to_bytes(4, "big")   # length of the first dimension's name
+    else:
+        # xCell's first dimension id -> 9999 (name record: length 5, "xCell", 3 pad bytes, then the rank and the ids)
+        i = raw.find(b"\x00\x00\x00\x05xCell\x00\x00\x00")
+        assert i > 0
+        pos = i + 12
+        assert int.from_bytes(raw[pos:pos + 4], "big") >= 1
+        raw[pos + 4:pos + 8] = (9999).to_bytes(4, "big")
+    open(path, "wb").write(bytes(raw))
+    code = ("import sys; sys.path.insert(0, %r); import pyMOPS; pyMOPS.MPASOReader.readGridData(%r)"
+            % (os.path.join(ROOT, "tools", "pyMOPS"), yaml))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and r.returncode > 0, (r.returncode, r.stderr[-500:])   # an exit / exception, not a signal
+    assert "netcdf" in r.stderr.lower(), r.stderr[-500:]
