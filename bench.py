@@ -612,10 +612,14 @@ def main():
         "unit": "Tinst/s (fp64-pipe thread instructions; DFMA, DMUL, DADD, DSETP each take one slot)",
         "frac": (fp64_per_step * rate / fp64_peak) if fp64_per_step else None,
         "traffic": traffic,
-        "kernel": prof.get("kernel", "mops::k_advect<6,true,3,false,false,true,true>"),
+        "kernel": prof.get("kernel", "void mops::k_advect<6, 1, 3, 0, 0, 1, 1, 1>(AdvectParams)"),
         "fp64_thread_inst_per_particle_step": fp64_per_step,
         "fp64_source": prof.get("source"),
         "peak_source": f"{info.sm_count} SMs x 64 fp64 lanes x {sm_max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json)",
+        "ncu": {k: prof.get(k) for k in ("fp64_pipe_active_pct_ncu", "l1_data_pipe_pct", "l1_hit_pct", "l2_hit_pct", "warps_active_pct",
+                                         "registers_per_thread", "dram_bytes_per_particle_step", "thread_inst_per_particle_step")},
+        "second_roof": "L1 data pipe (LSU write-back, 128 B/clk/SM): l1_data_pipe_pct of peak in the same capture; the kernel sits "
+                       "between the two, see DESIGN.md section 5",
         "kernel_ms_per_launch": float(np.mean(kms)) if kms else None,
         "kernel_particle_steps_per_s": rate,
         "kernel_share_of_step": (float(np.sum(kms)) / ms_local) if kms else None,
