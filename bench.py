@@ -521,6 +521,10 @@ def main():
         psteps_all = float(psteps)
     value = psteps_all / (ms_total / 1e3)
     executed_fraction = psteps_all / (float(n_total) * args.interval_steps * K)
+    per_step = torch.tensor(kern_steps, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(per_step, op=dist.ReduceOp.SUM)
+    executed_fraction_per_step = [float(x) / (float(n_total) * args.interval_steps) for x in per_step.tolist()]
 
     # ---- e2e arm: the HOST-memory form (submit / wait, pinned buffers, two sets) ----------------
     e2e = None
@@ -641,6 +645,7 @@ def main():
     config = {"workload": workload, "particles_total": n_total, "particles_this_rank": n,
               "cells": mesh.n_cells, "layers": L, "interval_steps": args.interval_steps,
               "executed_fraction": executed_fraction,
+              "executed_fraction_per_step": [round(x, 4) for x in executed_fraction_per_step] if args.chain else None,
               "near_edge_particles": near_edge,
               "l2_policy": "inputs larger than L2 (2 x 16.8 GB snapshots + particles); no flush needed",
               "semantics": "reference (RK4 stages in the start-of-step cell; particles stop at their first failed stage)",
