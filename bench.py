@@ -293,7 +293,8 @@ def main():
     ap.add_argument("--chain", action="store_true", help="feed end points back in instead of resetting the particles every step")
     ap.add_argument("--snapshot-upload", default="auto", choices=["auto", "replicated", "allgather"],
                     help="N > 1: 'allgather' = every rank uploads 1/N of the next snapshot over PCIe and an NCCL all-gather over "
-                         "NVLink completes it on every GPU; 'replicated' = every rank uploads the whole snapshot; auto = allgather")
+                         "NVLink completes it on every GPU; 'replicated' = every rank uploads the whole snapshot over its own PCIe "
+                         "link; auto = replicated (measured faster on the 8 x B200 box at N = 2 and N = 8, profiles/README.md)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -347,7 +348,7 @@ def main():
 
     # distinct host snapshots (pinned); snapshot s of the chain re-uses ring[s % len(ring)].  Two when host
     # memory allows (all ranks of the box pin theirs at once), else one.
-    use_ag = world > 1 and args.snapshot_upload in ("auto", "allgather")
+    use_ag = world > 1 and args.snapshot_upload == "allgather"
     snap_host_bytes = 3 * mesh.n_cells * L * 8
     ring_n = 2
     try:
@@ -447,9 +448,13 @@ def main():
     out_pos, out_vel = outs[0]
     io = ios[0]
     counts = sharding.all_counts(n, world, device=dev)
+    # one owner for the recorded trajectories needs 2 x n_total x each x 24 B on rank 0, and as much again for the receive
+    # staging: gathered while that fits beside the snapshots (C5 at 120-step intervals: 25 + 21 GB), otherwise the records
+    # stay sharded and only the end points travel (C5 at 720 steps would need 2 x 74 GB on one GPU)
+    gather_records = world > 1 and (4 * n_total * each * 24) < 70e9
     if world > 1:
         ends = [(torch.empty((n, 3), dtype=torch.float64, device=dev), torch.empty((n,), dtype=torch.float32, device=dev)) for _ in range(2)]
-        gathered = ([torch.empty((n_total, each, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+        gathered = (([torch.empty((n_total, each, 3), dtype=torch.float64, device=dev) for _ in range(2)] if gather_records else [None, None])
                     + [torch.empty((n_total, 3), dtype=torch.float64, device=dev), torch.empty((n_total,), dtype=torch.float32, device=dev)]
                     if rank == 0 else [None] * 4)
         k_done = [torch.cuda.Event() for _ in range(2)]
@@ -476,7 +481,8 @@ def main():
             ends[k][0].copy_(xyz); ends[k][1].copy_(depth)
             k_done[k].record()
             comm_stream.wait_event(k_done[k])
-            eng.dist_gather_traj(0, counts, perm, each, pos=outs[k][0], vel=outs[k][1], xyz=ends[k][0], depth=ends[k][1], n_total=n_total,
+            eng.dist_gather_traj(0, counts, perm, each, pos=outs[k][0] if gather_records else None, vel=outs[k][1] if gather_records else None,
+                                 xyz=ends[k][0], depth=ends[k][1], n_total=n_total,
                                  out_pos=gathered[0], out_vel=gathered[1], out_xyz=gathered[2], out_depth=gathered[3])
             g_done[k].record(comm_stream)
             g_used[k] = True
@@ -653,6 +659,10 @@ def main():
               "mesh_bytes": int(info.mesh_bytes), "snapshot_bytes": int(info.snapshot_bytes[0]),
               "parallelism": f"seeds sorted along the mesh's Morton curve and cut into {world} equal contiguous block(s), "
                              "mesh+snapshots replicated",
+              "trajectory_gather": (None if world == 1 else
+                                    "records + end points to rank 0 in caller order, NCCL send/recv inside the library (mops_dist_gather_traj), "
+                                    "overlapped with the next interval" if gather_records else
+                                    "end points only: the records of this configuration would not fit one GPU and stay sharded"),
               "snapshot_distribution": ("1/N PCIe upload per rank + NCCL all-gather" if use_ag
                                         else "whole snapshot uploaded by every rank")}
     torch.cuda.synchronize()

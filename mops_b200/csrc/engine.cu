@@ -420,8 +420,8 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
     if (wtop) CK(cudaMemcpyAsync(ctx->st_wtop.p, wtop, nC * (L + 1) * 8, kind_of(wtop), st));
 
     CK(cudaMemsetAsync(ctx->d_anyw + slot, 0, sizeof(int), st));
-    k_cell_ztop<<<blocks_for(ctx->nC, 128), 128, 0, st>>>((const double*)ctx->st_thick.p, (const double*)ctx->st_bottom.p,
-                                                          (double*)ctx->st_ztopc.p, ctx->nC, L);
+    k_cell_ztop<<<blocks_for(ctx->nC, CZ_CELLS), 128, (size_t)CZ_CELLS * (L + 1) * sizeof(double), st>>>(
+        (const double*)ctx->st_thick.p, (const double*)ctx->st_bottom.p, (double*)ctx->st_ztopc.p, ctx->nC, L);
     k_vertex_fields<<<blocks_for((long long)nV * L, 256), 256, 0, st>>>(
         ctx->vert, ctx->vcell_ext, ctx->trig, (const double*)ctx->st_ztopc.p, (const double*)ctx->st_zonal.p,
         (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L, ctx->d_anyw + slot);
