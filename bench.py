@@ -133,6 +133,32 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(device: int):
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
+    (first touch puts the pages there): with one process per GPU on a two-socket box the snapshot uploads and the trajectory
+    copy-backs otherwise cross the socket interconnect for half of the ranks.  Best effort: returns the node or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("0000") and len(bdf.split(":")[0]) == 8:   # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def make_snapshot_host(mesh, L, speed, tilt, pinned_alloc):
     """zonal / meridional / layerThickness / bottomDepth of a solid-body snapshot into (pinned) host arrays."""
     from mops_b200 import synthetic as S
@@ -333,6 +359,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -659,6 +686,7 @@ def main():
               "mesh_bytes": int(info.mesh_bytes), "snapshot_bytes": int(info.snapshot_bytes[0]),
               "parallelism": f"seeds sorted along the mesh's Morton curve and cut into {world} equal contiguous block(s), "
                              "mesh+snapshots replicated",
+              "numa_node_of_rank0": numa_node,
               "trajectory_gather": (None if world == 1 else
                                     "records + end points to rank 0 in caller order, NCCL send/recv inside the library (mops_dist_gather_traj), "
                                     "overlapped with the next interval" if gather_records else

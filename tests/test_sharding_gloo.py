@@ -100,3 +100,25 @@ def test_partitioned_snapshot_allgather(tmp_path):
     edges = [sharding.snapshot_part_bounds(flat.shape[0], r, world) for r in range(world)]
     assert edges[0][1] == 0 and edges[-1][2] == flat.shape[0]
     assert all(edges[r][2] == edges[r + 1][1] for r in range(world - 1))
+
+
+def test_morton_blocks_are_equal_and_contiguous_along_the_curve():
+    """product sharding (mops_order_key + mops_shard_bounds; here their Python twins): equal counts for a heavily skewed
+    key distribution, every block a contiguous range of the sorted keys, invalid keys (-1) last, every seed exactly once"""
+    from mops_b200 import sharding
+    rng = np.random.default_rng(4)
+    keys = np.concatenate([rng.integers(0, 50, 9000), rng.integers(0, 1_000_000, 1000), np.full(7, -1)]).astype(np.int32)
+    rng.shuffle(keys)
+    for world in (1, 2, 3, 8):
+        blocks = sharding.morton_blocks(keys, world)
+        sizes = [b.shape[0] for b in blocks]
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == keys.shape[0]
+        assert np.array_equal(np.sort(np.concatenate(blocks)), np.arange(keys.shape[0]))
+        u = keys.astype(np.uint32)
+        for a, b in zip(blocks[:-1], blocks[1:]):
+            if a.size and b.size:
+                assert u[a].max() <= u[b].min()
+        assert (keys[blocks[-1]][-7:] == -1).all()
+        for r in range(world):
+            lo, hi = sharding.block_bounds(keys.shape[0], r, world)
+            assert hi - lo == sizes[r]
