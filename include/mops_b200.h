@@ -194,9 +194,10 @@ typedef struct mops_traj_stats {
                                         ztop[-1] there (VK:1225, undefined behaviour); they keep their last position */
 } mops_traj_stats;
 
-/* Both calls integrate in launches of 40 steps (environment MOPS_SEGMENT_STEPS=<n>, 0 = one launch) with the
- * particles that stopped compacted away between launches -- results are identical either way.  The live count stays
- * on the device, so MOPS_MEM_DEVICE calls with stats = NULL are asynchronous on the context's stream whatever their
+/* Both calls integrate in launches of 40 steps with the particles that stopped compacted away between launches, or as
+ * one launch when the previous call's particles hardly ever stopped (the engine adapts; environment
+ * MOPS_SEGMENT_STEPS=<n> fixes the segment length, 0 = always one launch) -- results are identical either way.  The live
+ * count stays on the device, so MOPS_MEM_DEVICE calls with stats = NULL are asynchronous on the context's stream whatever their
  * length.  MOPS_MEM_HOST calls stage through device scratch and complete before they return; their asynchronous
  * form is submit / wait below. */
 /* replaces MOPS::Factory::StreamLine (src/Common/MOPSFactory.h:28-33 -> VK:653-1015) */

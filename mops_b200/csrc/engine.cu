@@ -85,6 +85,8 @@ struct mops_ctx {
     Buf s_state;            // AdvState[n]: parked loop state of the compacting multi-launch form
     int* d_nsel = nullptr;  // [2] number of live particles after a compaction (ping-pong: read by the next launch / compaction)
     int segment_steps = 40; // steps per launch of the compacting form; MOPS_SEGMENT_STEPS overrides (0 = one launch per call)
+    bool segment_forced = false; // MOPS_SEGMENT_STEPS was given: no adaptation
+    double stop_rate = -1.0;     // particles stopped per started step in the last call whose counters were read (< 0: unknown)
     Buf r_img0, r_img1, r_cells;
     unsigned long long* counters = nullptr; // [8]: particle-steps, alive at end, NaN pixels, near-edge particles, above-surface stops
     // HOST-mode trajectory calls: two sets of device staging + events, used alternately, so that the H2D of call k+1
@@ -98,6 +100,7 @@ struct mops_ctx {
         bool busy = false;       // a submitted call has not been waited for yet
         long long ticket = 0;    // its ticket
         long long launches = 0;  // kernels it launched
+        long long n = 0;         // its particle count
     } hset[2];
     long long host_seq = 0;      // tickets issued so far
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -568,7 +571,12 @@ int run_range(mops_ctx* ctx, const mops_traj_cfg* cfg, bool path, long long m, c
     P.n = m; P.order = d_order; P.cell0 = d_cell_int;
     P.step_begin = 0; P.step_end = P.times; P.state = nullptr; P.n_live = nullptr;
     if (ev_k0) CK(cudaEventRecord(ev_k0, st));
-    const int seg = ctx->segment_steps;
+    // Compaction pays when particles stop: a 40-step segment costs ~1.5 % (parked state, one select pass, the launch tails), a
+    // stopped particle's lane costs its share of every remaining step.  The rate at which the previous call's particles
+    // stopped predicts this one (chained intervals, repeated calls): below one stop per 4000 started steps (1.5 % of the
+    // particles over a 60-step half interval) the call runs as one launch.  Results do not depend on the choice.
+    int seg = ctx->segment_steps;
+    if (!ctx->segment_forced && ctx->stop_rate >= 0.0 && ctx->stop_rate < 2.5e-4) seg = 0;
     if (seg > 0 && P.times > seg && !(P.walk || P.diag_edge)) {
         // Compacting multi-launch form (default 40 steps per launch, MOPS_SEGMENT_STEPS=<steps>, 0 = off): under the reference's semantics particles
         // stop for good at their first failed stage, and a stopped particle's lane idles until its whole warp is
@@ -634,6 +642,8 @@ int host_wait(mops_ctx* ctx, long long ticket, int what, mops_traj_stats* stats)
     }
     CK(cudaEventSynchronize(S.out_done));
     S.busy = false;
+    if (S.h_counters[0] > 0)
+        ctx->stop_rate = (double)((unsigned long long)S.n - std::min<unsigned long long>(S.h_counters[1], (unsigned long long)S.n)) / (double)S.h_counters[0];
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->particle_steps = (int64_t)S.h_counters[0];
@@ -735,6 +745,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
             stats->alive_at_end = (int64_t)h_counters[1];
             stats->near_edge_particles = (int64_t)h_counters[3];
             stats->above_surface_particles = (int64_t)h_counters[4];
+            if (h_counters[0] > 0) ctx->stop_rate = (double)((unsigned long long)n - std::min<unsigned long long>(h_counters[1], (unsigned long long)n)) / (double)h_counters[0];
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev_kend) == cudaSuccess) stats->kernel_ms = ms;
             if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) stats->locate_ms = ms;
@@ -807,6 +818,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     S.busy = true;
     S.ticket = tk;
     S.launches = ctx->launches.load() - launches0;
+    S.n = n;
     if (ticket) {
         *ticket = tk;
         return MOPS_OK;
@@ -935,7 +947,7 @@ int mops_create(mops_ctx** out, int device_ordinal)
               cudaMalloc(&ctx->d_nonmono, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess &&
               cudaMalloc(&ctx->d_anyw, MOPS_MAX_SNAPSHOT_SLOTS * sizeof(int)) == cudaSuccess &&
               cudaMalloc(&ctx->d_nsel, 2 * sizeof(int)) == cudaSuccess;
-    if (const char* e = getenv("MOPS_SEGMENT_STEPS")) ctx->segment_steps = std::max(0, atoi(e));
+    if (const char* e = getenv("MOPS_SEGMENT_STEPS")) { ctx->segment_steps = std::max(0, atoi(e)); ctx->segment_forced = true; }
     ctx->stream = ctx->own_stream;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
