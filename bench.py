@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--snapshot-upload", default="auto", choices=["auto", "replicated", "allgather"],
                     help="N > 1: 'allgather' = every rank uploads 1/N of the next snapshot over PCIe and an NCCL all-gather over "
                          "NVLink completes it on every GPU; 'replicated' = every rank uploads the whole snapshot over its own PCIe "
-                         "link; auto = replicated (measured faster on the 8 x B200 box at N = 2 and N = 8, profiles/README.md)")
+                         "link; auto = replicated up to 4 GPUs, allgather beyond (measured on the 8 x B200 box, profiles/README.md)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -375,7 +375,10 @@ def main():
 
     # distinct host snapshots (pinned); snapshot s of the chain re-uses ring[s % len(ring)].  Two when host
     # memory allows (all ranks of the box pin theirs at once), else one.
-    use_ag = world > 1 and args.snapshot_upload == "allgather"
+    # auto: replicated uploads up to 4 GPUs, all-gather from 8 on.  Measured on the 8 x B200 box (profiles/README.md): at N = 8
+    # eight whole-snapshot uploads per interval (40 GB) crowd the host side of the e2e arm's own copies (e2e 18.3 G particle-steps/s
+    # replicated vs 26.5 G all-gather, device-resident 30.9 vs 28.3); at N = 2 replicated wins both (8.59 / 8.20 vs 8.34 / 7.95)
+    use_ag = world > 1 and (args.snapshot_upload == "allgather" or (args.snapshot_upload == "auto" and world > 4))
     snap_host_bytes = 3 * mesh.n_cells * L * 8
     ring_n = 2
     try:
