@@ -35,6 +35,7 @@ struct Snapshot {
     unsigned char* mono = nullptr;
     bool has_w = false;   // some velw record has a w component other than +0.0 (vertVelocityTop given and not all zero)
     bool w_known = true;  // false: async upload in flight, the device flag has not been read back yet
+    bool w_is_z = false;  // uploaded without vertVelocityTop: the w slot of every velw record holds zTop (SnapView::w_is_z)
     int nonmono = 0;
     size_t bytes = 0;
     cudaEvent_t ready = nullptr;    // recorded on the side stream after preprocessing
@@ -311,6 +312,7 @@ SnapView view_of(const Snapshot& s)
 {
     SnapView v;
     v.ztop = s.ztop; v.velw = s.velw; v.attr0 = s.attr[0]; v.attr1 = s.attr[1]; v.mono = s.mono;
+    v.w_is_z = s.w_is_z ? 1 : 0;
     return v;
 }
 
@@ -396,6 +398,7 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
     s.L = L;
     s.has_w = (wtop != nullptr);
     s.w_known = (wtop == nullptr);
+    s.w_is_z = (wtop == nullptr);
     s.n_attr = n_attr;
     s.n_attr_total = n_attr_total;
 
@@ -427,7 +430,8 @@ int set_snapshot_impl(mops_ctx* ctx, int slot, int L, const double* zonal, const
         (const double*)ctx->st_thick.p, (const double*)ctx->st_bottom.p, (double*)ctx->st_ztopc.p, ctx->nC, L);
     k_vertex_fields<<<blocks_for((long long)nV * L, 256), 256, 0, st>>>(
         ctx->vert, ctx->vcell_ext, ctx->trig, (const double*)ctx->st_ztopc.p, (const double*)ctx->st_zonal.p,
-        (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L, ctx->d_anyw + slot);
+        (const double*)ctx->st_merid.p, wtop ? (const double*)ctx->st_wtop.p : nullptr, s.ztop, s.velw, ctx->nV, L, ctx->d_anyw + slot,
+        wtop ? 0 : 1);
     ctx->launches += 2;
     for (int a = 0; a < n_attr; ++a) {
         CK(cudaMemcpyAsync(ctx->st_attr.p, attrs[a], nC * L * 8, kind_of(attrs[a]), st));
@@ -494,7 +498,7 @@ void dispatch_locate(mops_ctx* ctx, long long n, const double* d_xyz, int* d_cel
 // does not pay registers for either.  Resident 128-thread blocks per SM (register budget 65536 / (128 * MINB)):
 // 3 for the 6- and 8-wide records, 1 for the 20-wide ones -- from measurements on B200 (profiles/README.md:
 // 2 blocks 990 ms, 3 blocks 817 ms, 4 blocks 855 ms, 5 blocks 1065 ms, 6 blocks 1298 ms on the same step).
-template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false, bool NOW = false, bool FAST = false>
+template <int M, bool PATH, bool EXTRA, bool ATTR, bool SEG = false, int NOW = 0, bool FAST = false>
 void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 {
     const int grid = blocks_for(P.n, MOPS_ADV_BLOCK);
@@ -504,35 +508,40 @@ void launch_advect_inst(mops_ctx* ctx, const AdvectParams& P)
 
 // Production launches always use the SEG instantiation (a single launch is the segment [0, times) with no parked state); the
 // EXTRA instantiations (walk semantics / near-edge diagnostic) are single-launch only.  Hexagonal meshes (M == 6) without
-// attributes run the FAST instantiations (straight-line RK4 step, fastpath.cuh), in the NOW form when neither snapshot
-// carries vertVelocityTop.
+// attributes run the FAST instantiations (straight-line RK4 step, fastpath.cuh), in the NOW form that matches how the
+// snapshots store their vertical velocity (P.no_w).
+template <int M, bool PATH>
+void launch_fast(mops_ctx* ctx, const AdvectParams& P)
+{
+    constexpr bool HEX = (M == 6);
+    if (HEX && P.no_w == 2) launch_advect_inst<M, PATH, false, false, true, HEX ? 2 : 0, HEX>(ctx, P);
+    else if (HEX && P.no_w == 1) launch_advect_inst<M, PATH, false, false, true, HEX ? 1 : 0, HEX>(ctx, P);
+    else launch_advect_inst<M, PATH, false, false, true, 0, HEX>(ctx, P);
+}
+
 template <int M>
-void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path, bool now)
+void launch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
     const bool extra = P.walk || P.diag_edge;
     const bool attr = path && P.attr_count > 0 && P.out_attr;
-    constexpr bool HEX = (M == 6);
     if (!path) {
         if (extra) launch_advect_inst<M, false, true, false>(ctx, P);
-        else if (HEX && now) launch_advect_inst<M, false, false, false, true, HEX, HEX>(ctx, P);
-        else launch_advect_inst<M, false, false, false, true, false, HEX>(ctx, P);
+        else launch_fast<M, false>(ctx, P);
     } else if (attr) {
         if (extra) launch_advect_inst<M, true, true, true>(ctx, P);
         else launch_advect_inst<M, true, false, true, true>(ctx, P);
     } else {
         if (extra) launch_advect_inst<M, true, true, false>(ctx, P);
-        else if (HEX && now) launch_advect_inst<M, true, false, false, true, HEX, HEX>(ctx, P);
-        else launch_advect_inst<M, true, false, false, true, false, HEX>(ctx, P);
+        else launch_fast<M, true>(ctx, P);
     }
 }
 
 void dispatch_advect(mops_ctx* ctx, const AdvectParams& P, bool path)
 {
-    const bool now = P.no_w != 0;
     switch (ctx->M) {
-    case 6: launch_advect<6>(ctx, P, path, now); break;
-    case 8: launch_advect<8>(ctx, P, path, now); break;
-    default: launch_advect<20>(ctx, P, path, now); break;
+    case 6: launch_advect<6>(ctx, P, path); break;
+    case 8: launch_advect<8>(ctx, P, path); break;
+    default: launch_advect<20>(ctx, P, path); break;
     }
 }
 
@@ -708,7 +717,7 @@ int trajectory_impl(mops_ctx* ctx, const mops_traj_cfg* cfg, int front, int back
     P.rec = ctx->rec; P.c4 = ctx->c4; P.c_int2ext = ctx->c_int2ext; P.nC = ctx->nC; P.L = F.L;
     P.sv[0] = view_of(F); P.sv[1] = view_of(B);
     P.attr_count = attr_count;
-    P.no_w = (!F.has_w && !B.has_w) ? 1 : 0;
+    P.no_w = (!F.has_w && !B.has_w) ? ((F.w_is_z && B.w_is_z) ? 2 : 1) : 0;
     P.use_euler = (cfg->method == MOPS_METHOD_EULER) ? 1 : 0;
     P.delta_t = (cfg->direction == MOPS_DIR_FORWARD ? 1 : -1) * (int)cfg->delta_t;
     P.times = times; P.each = each; P.record_t = (int)cfg->record_t;
@@ -1230,7 +1239,7 @@ int mops_set_mesh(mops_ctx* ctx, int32_t n_cells, int32_t n_vertices, int32_t ma
 
     // keep the mesh records resident in L2 where the device allows it (access-policy window on
     // both streams; hitRatio scaled when the records exceed the persisting carve-out)
-    if (ctx->prop.persistingL2CacheMaxSize > 0 && ctx->prop.accessPolicyMaxWindowSize > 0) {
+    if (ctx->prop.persistingL2CacheMaxSize > 0 && ctx->prop.accessPolicyMaxWindowSize > 0 && !getenv("MOPS_NO_L2_WINDOW")) {
         const size_t rec_bytes = (ctx->M == 6 ? sizeof(CellRec<6>) : ctx->M == 8 ? sizeof(CellRec<8>) : sizeof(CellRec<20>)) * nC;
         const size_t carve = std::min<size_t>((size_t)ctx->prop.persistingL2CacheMaxSize, rec_bytes);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
@@ -1301,7 +1310,7 @@ int mops_get_prepared(mops_ctx* ctx, int32_t slot, double* ztop_vertex, double* 
     if (attr0_vertex && s.attr[0]) CK(cudaMalloc(&d_a0, nV * L * 8));
     if (attr1_vertex && s.attr[1]) CK(cudaMalloc(&d_a1, nV * L * 8));
     k_export_prepared<<<blocks_for((long long)nV * L, 256), 256, 0, ctx->stream>>>(ctx->v_ext2int, s.ztop, s.velw, s.attr[0], s.attr[1],
-                                                                                 d_z, d_v, d_w, d_a0, d_a1, ctx->nV, s.L);
+                                                                                 d_z, d_v, d_w, d_a0, d_a1, ctx->nV, s.L, s.w_is_z ? 1 : 0);
     ctx->launches++;
     CK(cudaGetLastError());
     if (d_z) CK(cudaMemcpyAsync(ztop_vertex, d_z, nV * L * 8, cudaMemcpyDeviceToHost, ctx->stream));

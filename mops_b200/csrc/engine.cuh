@@ -55,6 +55,9 @@ struct SnapView {
     const double* __restrict__ attr0;       // [nV][L] or null
     const double* __restrict__ attr1;
     const unsigned char* __restrict__ mono; // [nC] 1 = all vertex columns of the cell non-increasing
+    int w_is_z; // 1: the snapshot was uploaded without vertVelocityTop and the w slot of every velw record holds zTop of the
+                // same (vertex, level) instead of +0.0 (one 32-byte load then serves velocity AND the layer probe of the
+                // straight-line path); every reader of w substitutes 0.0
 };
 
 enum {
@@ -167,14 +170,17 @@ __device__ __forceinline__ void wachspress_weights(const CellRec<M>* __restrict_
 //  * roots, quotients and the reciprocal run as the branch-free exact sequences of dmath.cuh with ONE range decision at the
 //    end, so there is no slow-path merge inside the hot code.
 // ok = false: not covered (operands outside the windows, e.g. a point exactly on an edge) -> caller takes the generic path.
-template <int M>
+// LDG = true: the record is read with explicit ld.global.nc (the straight-line path launders `rec`, after which plain
+// dereferences compile to generic-space loads).
+template <int M, bool LDG = false>
 __device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, double px, double py, double pz, double (&w)[M], bool& ok)
 {
+    auto ld = [](const double* p) { return LDG ? ldg_f64(p) : *p; };
     double a[M];
     {
         double vx[M], vy[M], vz[M];
 #pragma unroll
-        for (int k = 0; k < M; ++k) { vx[k] = rec->vx[k]; vy[k] = rec->vy[k]; vz[k] = rec->vz[k]; }
+        for (int k = 0; k < M; ++k) { vx[k] = ld(&rec->vx[k]); vy[k] = ld(&rec->vy[k]); vz[k] = ld(&rec->vz[k]); }
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             const int kn = (k + 1) % M;
@@ -196,7 +202,7 @@ __device__ __forceinline__ void hex_weights(const CellRec<M>* __restrict__ rec, 
     unsigned wmn = 0xffffffffu, wmx = 0u;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        w[i] = div_by(rec->B[i], den[i], recip_refine(den[i]));
+        w[i] = div_by(ld(&rec->B[i]), den[i], recip_refine(den[i]));
         wmn = min(wmn, min(hi_raw(den[i]), hi_raw(w[i])));
         wmx = max(wmx, max(hi_raw(den[i]), hi_raw(w[i])));
     }
@@ -488,10 +494,9 @@ __device__ __forceinline__ void gather_velw(const double4* __restrict__ velw, co
 // levels `layer` (d*) and `layer - 1` (u*) of one snapshot in one pass over the vertices: one record pointer per
 // vertex, the upper level at a fixed -32 B offset.  Every accumulator sums in vertex order exactly as
 // gather_velw does, so the results are bit-equal to two gather_velw calls.
-// NOW = true (hexagon fast path of a snapshot uploaded WITHOUT vertVelocityTop): the w component of every record is +0.0 and
-// the weights are finite and positive, so both vertical sums are exactly +0.0 and are not accumulated.
-template <int M, bool FULL = false, bool NOW = false>
-__device__ __forceinline__ void gather_velw_pair(const double4* __restrict__ velw, const voff_t (&vo)[M], const double (&w)[M], int nv,
+// wz: the snapshot's w slots hold zTop (SnapView::w_is_z): the vertical velocity is +0.0 there.
+template <int M, bool FULL = false>
+__device__ __forceinline__ void gather_velw_pair(const double4* __restrict__ velw, bool wz, const voff_t (&vo)[M], const double (&w)[M], int nv,
                                                  int layer, double& dx, double& dy, double& dz, double& dw,
                                                  double& ux, double& uy, double& uz, double& uw)
 {
@@ -506,11 +511,11 @@ __device__ __forceinline__ void gather_velw_pair(const double4* __restrict__ vel
             dx += w[i] * d.x;
             dy += w[i] * d.y;
             dz += w[i] * d.z;
-            if (!NOW) dw += w[i] * d.w;
+            dw += w[i] * (wz ? 0.0 : d.w);
             ux += w[i] * u.x;
             uy += w[i] * u.y;
             uz += w[i] * u.z;
-            if (!NOW) uw += w[i] * u.w;
+            uw += w[i] * (wz ? 0.0 : u.w);
         }
     }
 }
@@ -552,8 +557,8 @@ struct EvalOut {
 // calc_velocity_at (streamline), VK:740-872.  Returns ST_ALIVE or the reason of failure.
 // FULL = true is the hexagon fast path (nv == M): it covers cells whose columns are monotone and points whose weight
 // arithmetic stays inside the exact-sequence windows, and returns ST_GENERIC for everything else (the caller then runs the
-// generic evaluation, FULL = false, which is the complete restatement).  NOW: see gather_velw_pair.
-template <int M, bool FULL = false, bool NOW = false>
+// generic evaluation, FULL = false, which is the complete restatement).
+template <int M, bool FULL = false>
 __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, const SnapView& s, bool mono, int L,
                                            const d3& p, double depth, int& hint, EvalOut& o)
 {
@@ -587,14 +592,14 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
     const double t = (x - ztop_dn) / denom;
 
     double dx, dy, dz, dw, ux, uy, uz, uw;
-    gather_velw_pair<M, FULL, FULL && NOW>(s.velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
+    gather_velw_pair<M, FULL>(s.velw, s.w_is_z != 0, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
     if (tiny_len(dx, dy, dz) || tiny_len(ux, uy, uz)) return ST_ZERO_VELOCITY; // VK:845-847
     const double omt = 1.0 - t;
     o.hx = t * ux + omt * dx; // VK:849
     o.hy = t * uy + omt * dy;
     o.hz = t * uz + omt * dz;
     if (tiny_len(o.hx, o.hy, o.hz)) return ST_ZERO_VELOCITY;
-    o.vv = (FULL && NOW) ? 0.0 : t * uw + omt * dw; // VK:870 (levels `layer`, `layer-1` of vertVelocityTop)
+    o.vv = t * uw + omt * dw; // VK:870 (levels `layer`, `layer-1` of vertVelocityTop)
     o.a0 = 0.0; o.a1 = 0.0;
     return ST_ALIVE;
 }
@@ -602,8 +607,8 @@ __device__ __forceinline__ int eval_stream(const CellRec<M>* __restrict__ rec, c
 // calc_velocity_at (pathline), VK:1124-1327: front and back interpolated separately (own layer
 // search each, shared weights), blended with alpha; no zero-velocity reject.  sv[0] = front,
 // sv[1] = back; the two snapshots go through ONE copy of the code (loops kept rolled) to
-// keep the kernel's instruction footprint down.  FULL / NOW as in eval_stream.
-template <int M, bool FULL = false, bool NOW = false>
+// keep the kernel's instruction footprint down.  FULL as in eval_stream.
+template <int M, bool FULL = false>
 __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv,
                                          bool mono_f, bool mono_b, int L, int attr_count, const d3& p, double depth,
                                          double alpha, int& hint_f, int& hint_b, EvalOut& o)
@@ -666,9 +671,9 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
         const double t = s ? t_back : t_front;
         const double omt = 1.0 - t;
         double dx, dy, dz, dw, ux, uy, uz, uw;
-        gather_velw_pair<M, FULL, FULL && NOW>(sv[s].velw, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
+        gather_velw_pair<M, FULL>(sv[s].velw, sv[s].w_is_z != 0, vo, w, nv, layer, dx, dy, dz, dw, ux, uy, uz, uw);
         const double vx = t * ux + omt * dx, vy = t * uy + omt * dy, vz = t * uz + omt * dz;
-        const double vw = (FULL && NOW) ? 0.0 : t * uw + omt * dw;
+        const double vw = t * uw + omt * dw;
         double a0 = 0.0, a1 = 0.0;
         if (attr_count >= 1) {
             const double ad = gather_scalar<M, FULL>(sv[s].attr0, vo, w, nv, layer), au = gather_scalar<M, FULL>(sv[s].attr0, vo, w, nv, layer - 1);
@@ -684,7 +689,7 @@ __device__ __forceinline__ int eval_path(const CellRec<M>* __restrict__ rec, con
             o.hx = alpha * vx + oma * ffx; // VK:1259
             o.hy = alpha * vy + oma * ffy;
             o.hz = alpha * vz + oma * ffz;
-            o.vv = (FULL && NOW) ? 0.0 : alpha * vw + oma * ffw; // VK:1286
+            o.vv = alpha * vw + oma * ffw; // VK:1286
             o.a0 = (attr_count >= 1) ? alpha * a0 + oma * fa0 : 0.0;
             o.a1 = (attr_count >= 2) ? alpha * a1 + oma * fa1 : 0.0;
         }

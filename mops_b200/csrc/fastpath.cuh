@@ -23,11 +23,11 @@ namespace mops {
 #ifndef MOPS_FAST_UNROLL_SNAP
 #define MOPS_FAST_UNROLL_SNAP 1
 #endif
-#ifndef MOPS_FAST_SPLIT_Z
-#define MOPS_FAST_SPLIT_Z 1
-#endif
 #ifndef MOPS_FAST_LOAD24
 #define MOPS_FAST_LOAD24 1
+#endif
+#ifndef MOPS_FAST_LDG
+#define MOPS_FAST_LDG 0 // 1 = explicit ld.global.nc for the (laundered) cell record instead of generic-space loads
 #endif
 
 // exact x / 6.0 of the RK4 combine; flags anything outside the window in which the correction step is exact
@@ -104,7 +104,11 @@ __device__ __forceinline__ d3 fast_rotate(const d3& pos, const d3& vel, double d
 // one snapshot's share of calc_velocity_at on a hexagon with known layer `h` (= the previous evaluation's layer): checks
 // that `h` is what the reference's search returns (engine.cuh, layer_search_stream / layer_search_path), forms t and
 // gathers + blends levels h, h-1 (VK:1229-1286 / VK:828-870).
-template <int M, bool PATH, bool NOW>
+// NOW (how the vertical velocity of the call's snapshots is stored): 0 = present (or mixed: per-snapshot `w_is_z` decides),
+// 1 = both snapshots without it, w slots hold +0.0: the vertical sums are exactly +0.0 and are not accumulated, 24-byte loads
+// of (vx,vy,vz); 2 = both without it and the w slot of a record holds zTop of that (vertex, level): one 32-byte load per
+// vertex and level serves velocity and layer probe (6 load instructions fewer per vertex than form 1, same bytes).
+template <int M, bool PATH, int NOW>
 __device__ __forceinline__ void fast_snapshot(const SnapView& s, const voff_t (&vo)[M], const double (&w)[M], int L, double depth, int hint,
                                               double& vx, double& vy, double& vz, double& vw, unsigned& bad)
 {
@@ -113,26 +117,20 @@ __device__ __forceinline__ void fast_snapshot(const SnapView& s, const voff_t (&
     bad |= (unsigned)(h != hint);
     double top = 0.0, bot = 0.0;
     double dx = 0.0, dy = 0.0, dz = 0.0, dw = 0.0, ux = 0.0, uy = 0.0, uz = 0.0, uw = 0.0;
-#if MOPS_FAST_SPLIT_Z
+    if (NOW != 2) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) { // VK:774-781 for levels h-1, h, vertex order
-        const double* __restrict__ zq = s.ztop + (vo[i] + (voff_t)h);
-        top += w[i] * zq[-1];
-        bot += w[i] * zq[0];
+        for (int i = 0; i < M; ++i) { // VK:774-781 for levels h-1, h, vertex order
+            const double* __restrict__ zq = s.ztop + (vo[i] + (voff_t)h);
+            top += w[i] * zq[-1];
+            bot += w[i] * zq[0];
+        }
     }
-#endif
+    const bool wz = (NOW == 0) && (s.w_is_z != 0);
 #pragma unroll
-    for (int i = 0; i < M; ++i) { // VK:774-781 for levels h-1, h and TK:128-164 for the same two levels, vertex order
-        const voff_t o = vo[i] + (voff_t)h;
-#if !MOPS_FAST_SPLIT_Z
-        const double* __restrict__ zq = s.ztop + o;
-        const double zt = zq[-1], zb = zq[0];
-        top += w[i] * zt;
-        bot += w[i] * zb;
-#endif
-        const double4* __restrict__ q = s.velw + o;
+    for (int i = 0; i < M; ++i) { // TK:128-164 for the same two levels, vertex order
+        const double4* __restrict__ q = s.velw + (vo[i] + (voff_t)h);
         double4 d, u;
-        if (NOW && MOPS_FAST_LOAD24) { // the w component is +0.0 and unused: 24-byte loads
+        if (NOW == 1 && MOPS_FAST_LOAD24) { // the w component is +0.0 and unused: 24-byte loads
             ldg_d3of4(q, d.x, d.y, d.z);
             ldg_d3of4(q - 1, u.x, u.y, u.z);
             d.w = 0.0; u.w = 0.0;
@@ -140,14 +138,18 @@ __device__ __forceinline__ void fast_snapshot(const SnapView& s, const voff_t (&
             d = ldg_d4(q);
             u = ldg_d4(q - 1);
         }
+        if (NOW == 2) { // w slot = zTop of (vertex, level)
+            top += w[i] * u.w;
+            bot += w[i] * d.w;
+        }
         dx += w[i] * d.x;
         dy += w[i] * d.y;
         dz += w[i] * d.z;
-        if (!NOW) dw += w[i] * d.w;
+        if (NOW == 0) dw += w[i] * (wz ? 0.0 : d.w);
         ux += w[i] * u.x;
         uy += w[i] * u.y;
         uz += w[i] * u.z;
-        if (!NOW) uw += w[i] * u.w;
+        if (NOW == 0) uw += w[i] * (wz ? 0.0 : u.w);
     }
     bool match = (depth <= top + eps) & (depth >= bot - eps);
     if (PATH) match = match & ((h == 1) | (depth < top - eps));              // first match of the linear scan (VK:1182-1218)
@@ -169,30 +171,31 @@ __device__ __forceinline__ void fast_snapshot(const SnapView& s, const voff_t (&
     vx = t * ux + omt * dx;
     vy = t * uy + omt * dy;
     vz = t * uz + omt * dz;
-    vw = NOW ? 0.0 : t * uw + omt * dw;
+    vw = (NOW != 0) ? 0.0 : t * uw + omt * dw;
 }
 
 // calc_velocity_at on a hexagon (nv == M), layers given by the hints.  PATH: front/back blended with alpha (VK:1124-1327);
 // else the streamline form (VK:740-872).
-template <int M, bool PATH, bool NOW>
+template <int M, bool PATH, int NOW>
 __device__ __forceinline__ void fast_eval(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv, int L, const d3& p, double depth,
                                           double alpha, int hint_f, int hint_b, double& hx, double& hy, double& hz, double& vv, unsigned& bad)
 {
     // IsInMesh (TK:40-53): any negative direction -> outside.  Sign bits are OR-ed (a -0.0 is sent to the generic path too).
     unsigned sgn = 0u;
+    auto ld = [](const double* q) { return MOPS_FAST_LDG ? ldg_f64(q) : *q; };
 #pragma unroll
     for (int k = 0; k < M; ++k) {
-        const double direction = rec->nx[k] * p.x + rec->ny[k] * p.y + rec->nz[k] * p.z;
+        const double direction = ld(&rec->nx[k]) * p.x + ld(&rec->ny[k]) * p.y + ld(&rec->nz[k]) * p.z;
         sgn |= hi_raw(direction);
     }
     bad |= sgn >> 31;
     double w[M];
     bool wok;
-    hex_weights<M>(rec, p.x, p.y, p.z, w, wok); // a non-finite p fails its windows
+    hex_weights<M, MOPS_FAST_LDG != 0>(rec, p.x, p.y, p.z, w, wok); // a non-finite p fails its windows
     bad |= (unsigned)!wok;
     voff_t vo[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) vo[i] = (voff_t)rec->vid[i] * (voff_t)L;
+    for (int i = 0; i < M; ++i) vo[i] = (voff_t)(MOPS_FAST_LDG ? ldg_s32(&rec->vid[i]) : rec->vid[i]) * (voff_t)L;
     if (PATH) {
         // front and back through ONE rolled copy of the snapshot code (FAST_UNROLL_SNAP = 2 interleaves them: more
         // independent chains, twice the gathered records in flight)
@@ -209,7 +212,7 @@ __device__ __forceinline__ void fast_eval(const CellRec<M>* __restrict__ rec, co
                 hx = alpha * bx + oma * fx; // VK:1259
                 hy = alpha * by + oma * fy;
                 hz = alpha * bz + oma * fz;
-                vv = NOW ? 0.0 : alpha * bw + oma * fw; // VK:1286
+                vv = (NOW != 0) ? 0.0 : alpha * bw + oma * fw; // VK:1286
             }
         }
     } else {
@@ -225,7 +228,7 @@ struct FastStep {
 };
 
 // One whole RK4 step (VK:931-986 / VK:1399-1465) in the start-of-step cell `rec`; returns bad (0 = results valid).
-template <int M, bool PATH, bool NOW>
+template <int M, bool PATH, int NOW>
 __device__ __forceinline__ unsigned fast_rk4_step(const CellRec<M>* __restrict__ rec, const SnapView* __restrict__ sv, int L, const d3& pos,
                                                   float depth_f, double alpha, double dalpha, int delta_t, int hint_f, int hint_b, FastStep& out)
 {
@@ -259,7 +262,7 @@ __device__ __forceinline__ unsigned fast_rk4_step(const CellRec<M>* __restrict__
             acc.x = acc.x + c * hx;
             acc.y = acc.y + c * hy;
             acc.z = acc.z + c * hz;
-            if (!NOW) vacc = vacc + c * vv;
+            if (NOW == 0) vacc = vacc + c * vv;
         }
         hprev = mk3(hx, hy, hz);
     }
@@ -267,7 +270,7 @@ __device__ __forceinline__ unsigned fast_rk4_step(const CellRec<M>* __restrict__
     hvel.x = fast_div6(acc.x, bad);
     hvel.y = fast_div6(acc.y, bad);
     hvel.z = fast_div6(acc.z, bad);
-    const double vvel = NOW ? 0.0 : fast_div6(vacc, bad);
+    const double vvel = (NOW != 0) ? 0.0 : fast_div6(vacc, bad);
     const double tx = pos.x + hvel.x * dt, ty = pos.y + hvel.y * dt, tz = pos.z + hvel.z * dt; // VK:962-964
     const double tl = fast_sqrt(tx * tx + ty * ty + tz * tz, bad);
     bad |= (unsigned)!(tl > 1e-12);

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128) k_cell_ztop(const double* __restrict__ th
 __global__ void k_vertex_fields(const VertRec* __restrict__ vert, const int* __restrict__ vcell_ext, const double4* __restrict__ trig,
                                 const double* __restrict__ ztop_c, const double* __restrict__ zonal, const double* __restrict__ merid,
                                 const double* __restrict__ wtop, double* __restrict__ ztop_v, double4* __restrict__ velw_v,
-                                int nV, int L, int* __restrict__ any_w)
+                                int nV, int L, int* __restrict__ any_w, int pack_z)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)nV * L) return;
@@ -251,9 +251,10 @@ __global__ void k_vertex_fields(const VertRec* __restrict__ vert, const int* __r
         o.w = r.u * wc[0] + r.v * wc[1] + r.w * wc[2];
     }
     ztop_v[idx] = zt;
-    velw_v[idx] = o;
-    // does the snapshot carry any vertical velocity?  (bit test: -0.0 and NaN count as "yes"; see gather_velw_pair NOW)
+    // does the snapshot carry any vertical velocity?  (bit test: -0.0 and NaN count as "yes")
     if (__double_as_longlong(o.w) != 0ll) *any_w = 1;
+    if (pack_z) o.w = zt; // no vertVelocityTop was given: the w slot carries zTop (SnapView::w_is_z)
+    velw_v[idx] = o;
 }
 
 // CalcCellCenterToVertex (ST:57-106): scalar attribute, clamped >= 0
@@ -310,7 +311,7 @@ __global__ void k_cell_mono(const CellRec<M>* __restrict__ rec, const unsigned c
 __global__ void k_export_prepared(const int* __restrict__ v_ext2int, const double* __restrict__ ztop_v, const double4* __restrict__ velw_v,
                                   const double* __restrict__ a0, const double* __restrict__ a1,
                                   double* __restrict__ o_ztop, double* __restrict__ o_vel, double* __restrict__ o_w,
-                                  double* __restrict__ o_a0, double* __restrict__ o_a1, int nV, int L)
+                                  double* __restrict__ o_a0, double* __restrict__ o_a1, int nV, int L, int w_is_z)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)nV * L) return;
@@ -321,7 +322,7 @@ __global__ void k_export_prepared(const int* __restrict__ v_ext2int, const doubl
     const double4 q = velw_v[src];
     if (o_vel) { o_vel[3 * idx] = q.x; o_vel[3 * idx + 1] = q.y; o_vel[3 * idx + 2] = q.z; }
     if (o_w) {
-        o_w[(size_t)ve * (L + 1) + k] = q.w;
+        o_w[(size_t)ve * (L + 1) + k] = w_is_z ? 0.0 : q.w;
         if (k == L - 1) o_w[(size_t)ve * (L + 1) + L] = 0.0;
     }
     if (o_a0 && a0) o_a0[idx] = a0[src];
@@ -339,7 +340,7 @@ struct AdvectParams {
     int nC, L;
     SnapView sv[2];   // [0] front, [1] back (pathline)
     int attr_count;   // pathline attributes in use (0..2)
-    int no_w;         // host-side dispatch only: neither snapshot carries vertVelocityTop (NOW instantiations)
+    int no_w;         // host-side dispatch only (fastpath.cuh NOW): 0 = vertical velocity present, 1 = absent, 2 = absent and the w slots hold zTop
     int use_euler;
     int delta_t;      // signed seconds
     int times;        // steps
@@ -578,10 +579,10 @@ __device__ __noinline__ StepIO step_generic_cold(const AdvectParams& P, int cell
 // ATTR = true carries the pathline's scalar attributes (P.attr_count > 0 and an output buffer).
 // SEG = true: the launch covers steps [P.step_begin, P.step_end) only (see AdvectParams::state); SEG = false is a
 // single-launch kernel (every SEG-only branch folds away at compile time).
-// NOW = true: neither snapshot of the call carries vertVelocityTop, see gather_velw_pair / fastpath.cuh.
+// NOW: how the vertical velocity of the call's snapshots is stored (0 present, 1 absent, 2 absent + zTop in the w slot), fastpath.cuh.
 // FAST = true (hexagonal meshes, no attributes, no diagnostics): RK4 steps on hexagons with monotone columns run the
 // straight-line form of fastpath.cuh; step_generic is called out of line for every step it does not cover.
-template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR, bool SEG = false, bool NOW = false, bool FAST = false>
+template <int M, bool PATH, int MINB, bool EXTRA, bool ATTR, bool SEG = false, int NOW = 0, bool FAST = false>
 __global__ void __launch_bounds__(MOPS_ADV_BLOCK, MINB) k_advect(const __grid_constant__ AdvectParams P)
 {
     static_assert(!FAST || (M == 6 && !EXTRA && !ATTR), "the straight-line path is the hexagon / no-attribute / no-diagnostic form");
