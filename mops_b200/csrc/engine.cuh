@@ -530,23 +530,8 @@ __device__ __forceinline__ double gather_scalar(const double* __restrict__ a, co
     return r;
 }
 
-#ifndef MOPS_SQ_FILTER
-#define MOPS_SQ_FILTER 0 // 1 = the streamline's zero-velocity tests decide on the squared norm when it is far from 1e-24; not yet measured
-#endif
-// MOPS_LENGTH(v) < 1e-12 (VK:845-852).  With the filter: sqrt is monotone and correctly rounded, so a squared norm
-// >= 2e-24 has a root >= 1.41e-12 and one <= 0.5e-24 a root <= 0.71e-12 -- only the band in between (and NaN, for which
-// both compares are false) takes the root, and the decision is the reference's in every case.
-__device__ __forceinline__ bool tiny_len(double x, double y, double z)
-{
-#if MOPS_SQ_FILTER
-    const double s = x * x + y * y + z * z;
-    if (s >= 2.0e-24) return false;
-    if (s <= 0.5e-24) return true;
-    return sqrt(s) < 1e-12;
-#else
-    return len3(x, y, z) < 1e-12;
-#endif
-}
+// MOPS_LENGTH(v) < 1e-12 (VK:845-852)
+__device__ __forceinline__ bool tiny_len(double x, double y, double z) { return len3(x, y, z) < 1e-12; }
 
 struct EvalOut {
     double hx, hy, hz; // horizontal velocity (XYZ)

@@ -115,3 +115,32 @@ def test_finalize_lines_threaded_equals_serial(monkeypatch):
     ref = P.finalize_lines(seeds, raw_pos, raw_vel, pathline_mode=True)
     for x, k in zip(out["8"], ("points", "velocity", "temperature", "salinity", "last")):
         assert np.array_equal(x, ref[k], equal_nan=True), k
+
+
+def test_shard_bounds_match_the_python_twin():
+    """mops_shard_bounds (pure host function of the C ABI) and mops_b200.sharding.block_bounds cut the same equal blocks"""
+    from mops_b200 import sharding
+    lib, capi = _lib()
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    for n in (0, 1, 7, 64_000_000, 10_000_001):
+        for world in (1, 2, 3, 8):
+            covered = 0
+            for r in range(world):
+                lib.mops_shard_bounds(n, r, world, ctypes.byref(lo), ctypes.byref(hi))
+                assert (lo.value, hi.value) == sharding.block_bounds(n, r, world)
+                assert lo.value == covered and hi.value - lo.value in (n // world, n // world + 1)
+                covered = hi.value
+            assert covered == n
+
+
+def test_multi_gpu_entry_points_fail_cleanly_without_devices():
+    """no GPU here: the multi-GPU constructors report MOPS_E_NODEVICE / invalid arguments instead of crashing, and there is
+    still no fallback of any kind"""
+    import torch
+    lib, capi = _lib()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    assert lib.mops_multi_create(ctypes.byref(h), 0, None) == -3 and not h.value
+    assert lib.mops_dist_create(ctypes.byref(h), None, 0, 1, None) == -1
+    assert lib.mops_multi_pathline(None, None, 0, 1, None, None) == -1
