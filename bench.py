@@ -7,7 +7,7 @@ solid-body-rotation snapshots, RK4, dt = 120 s, depth 800 m.  One bench "step" =
 MOPS_RunPathLine-equivalent call (mops_pathline through the C ABI) over one snapshot interval
 of `--interval-steps` RK4 steps (default 120 of the 720 a 1-day interval has, so that the
 default run ends within minutes; throughput is per particle-step), while the NEXT snapshot is
-uploaded + preprocessed on the side stream from pinned host memory (double-buffered H2D).
+uploaded + preprocessed on the side stream from pinned host memory (H2D double-buffered two intervals ahead).
 
 Every step integrates the SAME fresh seed set (particles are reset at the start of the step, a
 device-to-device copy inside the timed region): under the reference's semantics a particle stops
@@ -432,8 +432,13 @@ def main():
         eng.set_snapshot_raw(slot, L, h["zonal"].ctypes.data, h["merid"].ctypes.data, h["thick"].ctypes.data,
                              h["bottom"].ctypes.data, None, async_=async_)
 
+    # four resident slots: interval i integrates between slots i % 4 and (i + 1) % 4 while snapshot i + 3 is uploaded and
+    # preprocessed on the side stream, i.e. every snapshot has TWO intervals to arrive (at N = 8 an upload takes about as long
+    # as one 215 ms interval, and with one interval of slack the kernels waited ~20 ms per step for it)
+    NS = 4
     upload(0, 0, False)
     upload(1, 1, False)
+    upload(2, 2, False)
 
     # seeds: uniform on the sphere |lat| < 80 deg.  Sharding: the seed set is sorted along the mesh's
     # Morton curve (each seed's cell from the engine's own point location, cells ranked along the curve) and cut into
@@ -503,8 +508,8 @@ def main():
             torch.cuda.current_stream().wait_event(g_done[k])  # output set k is free again once its gather has run
         reset_particles()
         # next snapshot: async H2D + device preprocessing on the side stream (double buffering)
-        upload((i + 2) % 3, i + 2, True)
-        st = eng.traj_device(True, (i % 3, (i + 1) % 3), cfg_, ios[k] if io_ is io else io_, want_stats=True)
+        upload((i + 3) % NS, i + 3, True)
+        st = eng.traj_device(True, (i % NS, (i + 1) % NS), cfg_, ios[k] if io_ is io else io_, want_stats=True)
         if world > 1:
             # the path's one exchange: recorded trajectories + end points to rank 0 in caller order, NCCL over NVLink
             # (variable-size send/recv inside the library), on the comm stream so that it overlaps the next interval
@@ -591,8 +596,8 @@ def main():
                 else:
                     eng.traj_wait(tickets[i - 1], 0)                            # chain: the previous step's end points
                     hs["xyz"].copy_(sets[k ^ 1]["xyz"]); hs["depth"].copy_(sets[k ^ 1]["depth"])
-                upload((step_no + 2) % 3, step_no + 2, True)
-                tickets.append(eng.traj_submit(True, (step_no % 3, (step_no + 1) % 3), cfg_h, hs["io"]))
+                upload((step_no + 3) % NS, step_no + 3, True)
+                tickets.append(eng.traj_submit(True, (step_no % NS, (step_no + 1) % NS), cfg_h, hs["io"]))
                 step_no += 1
             for tk in tickets[max(0, count - 2):]:
                 ps += int(eng.traj_wait(tk, 1).particle_steps)
@@ -626,7 +631,7 @@ def main():
         xyz.copy_(seeds0); depth.fill_(DEPTH)
         cfg_e = capi.TrajCfg(capi.METHOD_RK4, capi.DIR_FORWARD, DT, duration, record_t, capi.MEM_DEVICE, sort, 1)
         torch.cuda.synchronize()
-        st_e = eng.traj_device(True, (step_no % 3, (step_no + 1) % 3), cfg_e, io, want_stats=True)
+        st_e = eng.traj_device(True, (step_no % NS, (step_no + 1) % NS), cfg_e, io, want_stats=True)
         te = torch.tensor([float(st_e.near_edge_particles)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.SUM)
