@@ -20,8 +20,9 @@
  *    throws across the boundary.  There is NO CPU fallback: without a CUDA device (or if
  *    the sm_100a kernels cannot be loaded) mops_create fails.
  *  - one context = one GPU = one caller thread at a time (the reference API is not
- *    re-entrant either).  Multi-GPU = one context per process/GPU with the
- *    mesh replicated and particles sharded by the caller (bench.py, torch.distributed).
+ *    re-entrant either); the one exception is mops_set_snapshot_async for a
+ *    slot no running call uses, which may come from a second host thread.  Multi-GPU: the
+ *    mops_dist_* (one process per GPU) and mops_multi_* (one process, N GPUs) sections below.
  *  - connectivity is passed exactly as MPAS files / MPASOGrid hold it: int32, 1-based,
  *    0-padded rows of width maxEdges (src/IO/MPASOReader.cpp:147-153).  Cell ids that
  *    cross this boundary in either direction are 0-based indices into the caller's cell
