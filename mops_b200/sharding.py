@@ -12,7 +12,8 @@ import numpy as np
 
 
 def longitude_sector(xyz: np.ndarray, world: int) -> np.ndarray:
-    """sector id in [0, world) of every particle: equal-width longitude wedges"""
+    """sector id in [0, world) of every particle: equal-width longitude wedges (round 1's sharding; balanced only for
+    uniform seeds -- bench.py and the product use morton_blocks / mops_order_key now; kept for engine-less callers)"""
     lon = np.arctan2(xyz[:, 1], xyz[:, 0])
     return np.minimum(((lon + np.pi) / (2.0 * np.pi) * world).astype(np.int64), world - 1)
 
